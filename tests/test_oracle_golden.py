@@ -1,0 +1,93 @@
+"""The oracle (oracle/sgmcmc_oracle.py) against the golden call traces recorded
+from the unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import sgmcmc_oracle as O
+from replay import GOLDEN_DIR, OracleEngine, Trace, replay
+
+TRACES = ["sgld_trace", "sgld_nomomentum_trace", "verlet_trace", "hmc_trace",
+          "runner_verlet_normal_trace", "runner_verlet_laplace_trace",
+          "runner_verlet_studentt_trace"]
+
+# fp32 elementwise work replayed op for op: a few ulp of drift over <=100 calls
+TRAJ_TOL = 1e-5
+SCALAR_TOL = 1e-5
+DE_ABS_TOL = 1e-4
+
+
+def _check(rep):
+    assert rep.n_events > 0
+    assert rep.p_err < TRAJ_TOL and rep.m_err < TRAJ_TOL, rep
+    assert rep.decisions_equal == rep.decisions, rep
+    assert rep.de_abs_err < DE_ABS_TOL, rep
+    assert rep.log_accept_err < 10 * DE_ABS_TOL, rep
+    for k, v in rep.scalar_err.items():
+        assert v < SCALAR_TOL, (k, v)
+
+
+@pytest.mark.parametrize("name", TRACES)
+@pytest.mark.parametrize("dot_dtype", [np.float32, np.float64])
+def test_oracle_reproduces_reference_trace(name, dot_dtype):
+    t = Trace(name)
+    _check(replay(t, OracleEngine(t, dot_dtype=dot_dtype)))
+
+
+@pytest.mark.parametrize("name", [n for n in TRACES if n.startswith("runner")])
+def test_oracle_fused_prior_reproduces_reference_trace(name):
+    """Likelihood-only gradient in, closed-form prior gradient added by the
+    oracle: must land on the reference trajectory, whose p.grad came from
+    autograd through Prior.log_prob (prior/base.py:57-58)."""
+    t = Trace(name)
+    _check(replay(t, OracleEngine(t, fused_prior=True), fused_prior=True))
+
+
+def test_runner_trace_has_the_call_order_of_the_reference_runner():
+    """inference_reject.py:57-59 then, per sampling epoch, :120-127,:156."""
+    t = Trace("runner_verlet_studentt_trace")
+    ops = [e["op"] for e in t.events]
+    assert ops[:2] == ["sample_momentum", "initial_step"]
+    for i, op in enumerate(ops):
+        if op == "maybe_reject":
+            assert ops[i - 2:i] == ["final_step", "delta_energy"]
+            assert ops[i + 1] == "initial_step"
+    assert any(e["op"] == "maybe_reject" and e["out"][0] for e in t.events)
+    assert any(e["op"] == "maybe_reject" and not e["out"][0] for e in t.events)
+
+
+def test_priors_against_reference_log_prob_and_autograd():
+    z = np.load(os.path.join(GOLDEN_DIR, "priors.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    assert {m["kind"] for m in meta} == {1, 2, 3}
+    for m in meta:
+        p, g = z[m["name"] + "_p"], z[m["name"] + "_grad"]
+        lp = O.prior_log_prob(m["kind"], p, m["loc"], m["scale"], m.get("df", 3.0))
+        assert math.isclose(lp, m["log_prob"], rel_tol=2e-6), (m["name"], lp, m["log_prob"])
+        got = O.prior_grad_log_prob(m["kind"], p, m["loc"], m["scale"], m.get("df", 3.0))
+        np.testing.assert_allclose(got, g, rtol=3e-6, atol=1e-30, err_msg=m["name"])
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    def run(c, k):
+        r = O.philox4x32_10(*[np.array([x], dtype=np.uint32) for x in c], k[0], k[1])
+        return [int(x[0]) for x in r]
+    assert run((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert run((0xffffffff,) * 4, (0xffffffff,) * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert run((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_normal_is_standard_normal():
+    import scipy.stats
+    z = O.philox_normal(O.philox_key(7, 3), 11, np.arange(50000)).reshape(-1).astype(np.float64)
+    assert np.isfinite(z).all()
+    assert scipy.stats.kstest(z, "norm").pvalue > 0.01
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    # different launch counters / keys decorrelate
+    z2 = O.philox_normal(O.philox_key(7, 3), 12, np.arange(50000)).reshape(-1)
+    assert abs(np.corrcoef(z, z2)[0, 1]) < 0.01
