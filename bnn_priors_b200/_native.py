@@ -1,0 +1,143 @@
+"""ctypes binding of the C ABI in include/bnnp.h (libbnnp.so, built in-tree by
+`bnn_priors_b200.build`).  Nothing here computes: it only describes the structs
+and forwards calls.  If the library is missing the import of the sampler classes
+fails loudly -- there is no other implementation of the path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libbnnp.so")
+
+# ---- constants of include/bnnp.h (tests/test_abi.py checks them against the header)
+ABI_VERSION = 2
+SEG_ALIGN = 32
+THREADS = 256
+UNROLL = 4
+CHUNK = THREADS * UNROLL * 4
+NRED = 8
+STATE_STRIDE = 16
+
+PRIOR_NONE, PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T = 0, 1, 2, 3
+OP_SGLD, OP_VERLET, OP_HMC, OP_SAMPLE_MOMENTUM, OP_REDUCE = 0, 1, 2, 3, 4
+PHASE_INITIAL, PHASE_MID, PHASE_FINAL = 0, 1, 2
+NOISE_NONE, NOISE_REPLAY, NOISE_PHILOX = 0, 1, 2
+
+F_READ_P = 1 << 0
+F_READ_G = 1 << 1
+F_READ_M = 1 << 2
+F_WRITE_P = 1 << 3
+F_WRITE_M = 1 << 4
+F_SAVE_STATE = 1 << 5
+F_CALC_METRICS = 1 << 6
+F_LOG_PRIOR = 1 << 7
+F_CLAMP_GRAD = 1 << 8
+F_NOISE_FIRST = 1 << 9
+F_MM_PRE_NOISE = 1 << 10
+F_UPDATE_SQ = 1 << 11
+F_PRIOR_GRAD = 1 << 12
+
+(S_DELTA_ENERGY, S_PREV_NEW_MOM, S_EST_MM, S_EST_PG, S_SUM_GG, S_SUM_MM, S_SQ_MEAN,
+ S_LOG_PRIOR, S_GM_OLD, S_GM_NEW, S_MM_OLD, S_MM_NEW, S_NONFINITE, S_LAUNCHES) = range(14)
+
+# BnnpSegment as a numpy record (the table is built on the host and copied to HBM)
+SEGMENT_DTYPE = np.dtype([
+    ("off", np.int64), ("numel", np.int64), ("precond", np.float64),
+    ("prior_loc", np.float32), ("prior_scale", np.float32), ("prior_df", np.float32),
+    ("prior_kind", np.int32), ("first_chunk", np.int32), ("num_chunks", np.int32)], align=True)
+assert SEGMENT_DTYPE.itemsize == 48
+
+
+class BnnpLaunch(C.Structure):
+    _fields_ = [
+        ("P", C.c_void_p), ("G", C.c_void_p), ("M", C.c_void_p),
+        ("prev_p", C.c_void_p), ("prev_g", C.c_void_p), ("prev_m", C.c_void_p),
+        ("replay_noise", C.c_void_p),
+        ("segs", C.c_void_p), ("chunk_seg", C.c_void_p), ("seg_state", C.c_void_p),
+        ("partials", C.c_void_p), ("tickets", C.c_void_p),
+        ("nseg", C.c_int32), ("nchunks", C.c_int32),
+        ("op", C.c_int32), ("phase", C.c_int32), ("noise", C.c_int32),
+        ("flags", C.c_uint32), ("key0", C.c_uint32), ("key1", C.c_uint32),
+        ("call", C.c_uint64),
+        ("cm", C.c_double), ("cg", C.c_double), ("cn", C.c_double), ("cp", C.c_double),
+        ("inv_num_data", C.c_double), ("grad_max", C.c_double),
+        ("c_gm_base", C.c_double), ("curv_base", C.c_double), ("rms_alpha", C.c_double),
+    ]
+
+
+EXPORTS = ("bnnp_abi_version", "bnnp_last_error", "bnnp_device_info", "bnnp_max_ctas_per_sm",
+           "bnnp_plan_layout", "bnnp_launch", "bnnp_rollback")
+
+
+class BnnpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libbnnp.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BnnpError(
+            f"{LIB_PATH} is missing: build it with `python -m bnn_priors_b200.build` "
+            "(nvcc, sm_100a).  bnn_priors_b200 has no fallback implementation.")
+    l = C.CDLL(LIB_PATH)
+    l.bnnp_abi_version.restype = C.c_int
+    l.bnnp_last_error.restype = C.c_char_p
+    l.bnnp_device_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    l.bnnp_max_ctas_per_sm.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    l.bnnp_plan_layout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p]
+    l.bnnp_launch.argtypes = [C.POINTER(BnnpLaunch), C.c_void_p]
+    l.bnnp_rollback.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
+    for name in EXPORTS:
+        getattr(l, name)          # AttributeError if a symbol is missing
+    if l.bnnp_abi_version() != ABI_VERSION:
+        raise BnnpError(f"libbnnp.so has ABI {l.bnnp_abi_version()}, this package expects {ABI_VERSION}; rebuild")
+    _lib = l
+    return l
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise BnnpError(f"{what} failed ({rc}): {lib().bnnp_last_error().decode()}")
+
+
+def plan_layout(numels):
+    """Host-side layout planner (bnnp_plan_layout).  Returns
+    (off[nseg], first_chunk[nseg], num_chunks[nseg], total_elems, chunk_seg[nchunks])."""
+    numel = np.ascontiguousarray(numels, dtype=np.int64)
+    n = int(numel.size)
+    off = np.zeros(n, np.int64)
+    first = np.zeros(n, np.int32)
+    nch = np.zeros(n, np.int32)
+    total, chunks = C.c_int64(0), C.c_int32(0)
+    l = lib()
+    check(l.bnnp_plan_layout(numel.ctypes.data, n, off.ctypes.data, first.ctypes.data, nch.ctypes.data,
+                             C.byref(total), C.byref(chunks), None), "bnnp_plan_layout")
+    chunk_seg = np.zeros(max(chunks.value, 1), np.int32)
+    check(l.bnnp_plan_layout(numel.ctypes.data, n, off.ctypes.data, first.ctypes.data, nch.ctypes.data,
+                             C.byref(total), C.byref(chunks), chunk_seg.ctypes.data), "bnnp_plan_layout")
+    return off, first, nch, int(total.value), chunk_seg[:chunks.value]
+
+
+# ---- Philox key schedule (specified in oracle/sgmcmc_oracle.py:philox_key) -------------
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+def philox_key(seed: int, stream: int):
+    k = _splitmix64((seed + stream * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+    return k & 0xFFFFFFFF, k >> 32

@@ -1,0 +1,511 @@
+// bnnp_kernels.cu -- the SG-MCMC sampler step for B200 (sm_100a) behind the C ABI
+// declared in include/bnnp.h.
+//
+// One kernel family does every sampler transition of the reference
+// (bnn_priors/mcmc/sgld.py:119-154, verlet_sgld.py:149-197, hmc.py:41-79,
+// sample_momentum sgld.py:57-69) in ONE pass over the flat parameter / gradient /
+// momentum arrays:  128-bit loads of p, g, m  ->  (optional) closed-form prior
+// gradient (prior/loc_scale.py:34-77)  ->  noise from an in-register Philox4x32-10
+// + Box-Muller (or a replay buffer for parity tests)  ->  momentum and parameter
+// update  ->  128-bit stores of p', m' (and the verlet_sgld.py:72-83 snapshot)  ->
+// eight dot products per chunk, reduced warp -> CTA -> segment in a fixed order.
+// The last CTA of every segment (ticket counter) folds the chunk partials in fp64
+// and applies the sampler's scalar bookkeeping (delta_energy,
+// prev_new_momentum_delta, est_temperature, est_config_temp, square_avg mean) on
+// the device, so the host never has to synchronise unless it wants a scalar.
+//
+// The path is HBM-bound elementwise work: no tensor cores, no shared-memory tiles;
+// what matters is coalesced 16-byte accesses, enough loads in flight per SM and a
+// lean instruction stream for the Philox rounds.
+
+#include "bnnp.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+
+constexpr int THREADS = BNNP_THREADS;
+constexpr int UNROLL = BNNP_UNROLL;
+constexpr int CHUNK = BNNP_CHUNK;
+constexpr int NWARPS = THREADS / 32;
+static_assert(NWARPS == BNNP_NRED, "the segment epilogue maps one warp to one partial sum");
+
+// indices of the per-chunk partial sums
+enum { R_GM_OLD = 0, R_GM_NEW, R_MM_OLD, R_MM_NEW, R_PG, R_GG, R_LOGP, R_NONFINITE };
+
+// ---------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) and the Box-Muller transform specified in
+// oracle/sgmcmc_oracle.py:_box_muller.  The round keys are uniform per launch and
+// are precomputed by the caller of philox_normal4.
+// ---------------------------------------------------------------------------------
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+
+__device__ __forceinline__ PhiloxKeys philox_round_keys(uint32_t key0, uint32_t key1) {
+    PhiloxKeys k;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        k.k0[r] = key0 + 0x9E3779B9u * (uint32_t)r;
+        k.k1[r] = key1 + 0xBB67AE85u * (uint32_t)r;
+    }
+    return k;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                              const PhiloxKeys& k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k.k0[r];
+        const uint32_t n2 = hi0 ^ c3 ^ k.k1[r];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+}
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float& z0, float& z1) {
+    const float u = fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0, 1]
+    const float t = fmaf(__uint2float_rn(y), 2.3283064365386963e-10f, -0.5f);                     // [-.5, .5]
+    const float theta = t * 6.283185307179586f;
+    const float r = fast_sqrt(-2.0f * __logf(u));
+    float s, c;
+    __sincosf(theta, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// four N(0,1) for the flat element quad `quad` of launch `call`
+__device__ __forceinline__ void philox_normal4(uint64_t quad, uint64_t call, const PhiloxKeys& k, float z[4]) {
+    uint32_t c0 = (uint32_t)quad, c1 = (uint32_t)(quad >> 32);
+    uint32_t c2 = (uint32_t)call, c3 = (uint32_t)(call >> 32);
+    philox4x32_10(c0, c1, c2, c3, k);
+    box_muller(c0, c1, z[0], z[1]);
+    box_muller(c2, c3, z[2], z[3]);
+}
+
+// ---------------------------------------------------------------------------------
+// Priors.  Per-segment constants (uniform over the CTA).
+// ---------------------------------------------------------------------------------
+struct PriorConst {
+    int kind;
+    float loc;
+    float k;        // NORMAL: 1/(N s^2); LAPLACE: 1/(N s); STUDENT_T: 1/N
+    float a, b;     // STUDENT_T: a = df + 1, b = df s^2;  log-prob: see log_prior_term
+    float inv_s;    // 1/s
+    float inv_df;
+};
+
+__device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double inv_n) {
+    PriorConst pc;
+    pc.kind = sd.prior_kind;
+    pc.loc = sd.prior_loc;
+    const float s = sd.prior_scale, df = sd.prior_df;
+    pc.inv_s = 1.0f / s;
+    pc.inv_df = 1.0f / df;
+    pc.a = df + 1.0f;
+    pc.b = df * s * s;
+    if (pc.kind == BNNP_PRIOR_NORMAL) pc.k = (float)(inv_n / ((double)s * (double)s));
+    else if (pc.kind == BNNP_PRIOR_LAPLACE) pc.k = (float)(inv_n / (double)s);
+    else pc.k = (float)inv_n;
+    return pc;
+}
+
+// -(1/N) d log p / d theta: what potential = loss - log_prior/N (models/base.py:76)
+// adds to p.grad through autograd in the reference.
+__device__ __forceinline__ float prior_grad_term(const PriorConst& pc, float p) {
+    const float d = p - pc.loc;
+    if (pc.kind == BNNP_PRIOR_NORMAL) return d * pc.k;
+    if (pc.kind == BNNP_PRIOR_LAPLACE) return d == 0.0f ? 0.0f : copysignf(pc.k, d);
+    if (pc.kind == BNNP_PRIOR_STUDENT_T) return (pc.a * d) / fmaf(d, d, pc.b) * pc.k;
+    return 0.0f;
+}
+
+// the theta-dependent part of log p(theta); the per-element constant is added once
+// per segment in the epilogue (log_prior_const)
+__device__ __forceinline__ float log_prior_term(const PriorConst& pc, float p) {
+    const float z = (p - pc.loc) * pc.inv_s;
+    if (pc.kind == BNNP_PRIOR_NORMAL) return -0.5f * z * z;
+    if (pc.kind == BNNP_PRIOR_LAPLACE) return -fabsf(z);
+    if (pc.kind == BNNP_PRIOR_STUDENT_T) return -0.5f * pc.a * log1pf(z * z * pc.inv_df);
+    return 0.0f;
+}
+
+__device__ double log_prior_const(const BnnpSegment& sd) {
+    const double s = (double)sd.prior_scale, df = (double)sd.prior_df;
+    if (sd.prior_kind == BNNP_PRIOR_NORMAL) return -log(s) - 0.9189385332046727;  // .5 log 2pi
+    if (sd.prior_kind == BNNP_PRIOR_LAPLACE) return -log(2.0 * s);
+    if (sd.prior_kind == BNNP_PRIOR_STUDENT_T)
+        return -(log(s) + 0.5 * log(df) + 0.5723649429247001 /* .5 log pi */ + lgamma(0.5 * df) -
+                 lgamma(0.5 * (df + 1.0)));
+    return 0.0;
+}
+
+// ---------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------
+union F4 {
+    float4 v;
+    float f[4];
+};
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_f4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct Coef {
+    float cm, cgM, cn, cpM, gmax;
+};
+
+// One float4 of every stream.  MASKED is the (rare) quad that straddles the end of
+// its segment: lanes >= `valid` are padding and must come out as zeros.
+template <int NOISE, bool PRIOR, bool MASKED>
+__device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c, const PriorConst& pc, int valid,
+                                            F4& p, const F4& g, F4& m, const float eps[4], float acc[BNNP_NRED]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool ok = !MASKED || j < valid;
+        const float p0 = ok ? p.f[j] : 0.0f;
+        const float m0 = ok ? m.f[j] : 0.0f;
+        float gj = ok ? g.f[j] : 0.0f;
+        const float e = (NOISE != BNNP_NOISE_NONE && ok) ? eps[j] : 0.0f;
+        acc[R_NONFINITE] = fmaf(gj, 0.0f, acc[R_NONFINITE]);   // 0, or NaN once g is inf/NaN
+        if (PRIOR) {
+            if ((flags & BNNP_F_PRIOR_GRAD) && ok) gj += prior_grad_term(pc, p0);
+            if (flags & BNNP_F_CLAMP_GRAD) gj = fminf(fmaxf(gj, -c.gmax), c.gmax);
+        }
+        float t, pre;
+        if (flags & BNNP_F_NOISE_FIRST) {
+            t = c.cn * e;
+            t = fmaf(c.cgM, gj, t);
+            if (c.cm != 0.0f) t = fmaf(c.cm, m0, t);
+            pre = t;
+        } else {
+            t = c.cm * m0;
+            t = fmaf(c.cgM, gj, t);
+            pre = t;
+            if (NOISE != BNNP_NOISE_NONE) t = fmaf(c.cn, e, t);
+        }
+        acc[R_GM_OLD] = fmaf(gj, m0, acc[R_GM_OLD]);
+        acc[R_GM_NEW] = fmaf(gj, t, acc[R_GM_NEW]);
+        const float mo = (flags & BNNP_F_MM_PRE_NOISE) ? pre : m0;
+        acc[R_MM_OLD] = fmaf(mo, mo, acc[R_MM_OLD]);
+        acc[R_MM_NEW] = fmaf(t, t, acc[R_MM_NEW]);
+        acc[R_PG] = fmaf(p0, gj, acc[R_PG]);
+        acc[R_GG] = fmaf(gj, gj, acc[R_GG]);
+        const float pn = (flags & BNNP_F_WRITE_P) ? fmaf(c.cpM, t, p0) : p0;
+        if (PRIOR) {
+            if ((flags & BNNP_F_LOG_PRIOR) && ok) acc[R_LOGP] += log_prior_term(pc, pn);
+        }
+        p.f[j] = pn;
+        m.f[j] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// The step kernel: one CTA per chunk of BNNP_CHUNK floats of one segment.
+// ---------------------------------------------------------------------------------
+template <int NOISE, bool PRIOR>
+__global__ void __launch_bounds__(THREADS) bnnp_step_kernel(const BnnpLaunch L) {
+    __shared__ double s_red[NWARPS][BNNP_NRED];
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.x;
+    const int seg = L.chunk_seg[chunk];
+    const BnnpSegment sd = L.segs[seg];
+    const int64_t cbase = (int64_t)(chunk - sd.first_chunk) * CHUNK;
+    const int64_t left = sd.numel - cbase;
+    const int rem = left < (int64_t)CHUNK ? (int)left : CHUNK;   // valid floats in this chunk
+    const int64_t fbase = sd.off + cbase;                          // flat index of the chunk
+    const uint32_t flags = L.flags;
+
+    Coef c;
+    c.cm = (float)L.cm;
+    c.cn = (float)L.cn;
+    c.cgM = (float)(L.cg * sd.precond);
+    c.cpM = (float)(L.cp * sd.precond);
+    c.gmax = (float)L.grad_max;
+    PriorConst pc;
+    pc.kind = BNNP_PRIOR_NONE;
+    if (PRIOR) pc = make_prior(sd, L.inv_num_data);
+
+    PhiloxKeys keys;
+    if (NOISE == BNNP_NOISE_PHILOX) keys = philox_round_keys(L.key0, L.key1);
+
+    // ---- front-batched 128-bit loads: up to 3 (4 with replay noise) x UNROLL in flight per thread
+    F4 p[UNROLL], g[UNROLL], m[UNROLL], z[UNROLL];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int e = (u * THREADS + tid) * 4;
+        const bool act = e < rem;
+        p[u].v = (act && (flags & BNNP_F_READ_P)) ? ld_f4(L.P + fbase + e) : zero4;
+        g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_f4(L.G + fbase + e) : zero4;
+        m[u].v = (act && (flags & BNNP_F_READ_M)) ? ld_f4(L.M + fbase + e) : zero4;
+        if (NOISE == BNNP_NOISE_REPLAY) z[u].v = act ? ld_f4(L.replay_noise + fbase + e) : zero4;
+    }
+
+    float acc[BNNP_NRED];
+#pragma unroll
+    for (int k = 0; k < BNNP_NRED; ++k) acc[k] = 0.0f;
+
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int e = (u * THREADS + tid) * 4;
+        if (e >= rem) continue;
+        if (flags & BNNP_F_SAVE_STATE) {   // verlet_sgld.py:72-83, the values BEFORE the update
+            st_f4(L.prev_p + fbase + e, p[u].v);
+            st_f4(L.prev_g + fbase + e, g[u].v);
+            if (L.prev_m != nullptr) st_f4(L.prev_m + fbase + e, m[u].v);
+        }
+        if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)(fbase + e) >> 2, L.call, keys, z[u].f);
+        const int valid = rem - e;
+        if (valid >= 4) update_quad<NOISE, PRIOR, false>(flags, c, pc, 4, p[u], g[u], m[u], z[u].f, acc);
+        else update_quad<NOISE, PRIOR, true>(flags, c, pc, valid, p[u], g[u], m[u], z[u].f, acc);
+        if (flags & BNNP_F_WRITE_P) st_f4(L.P + fbase + e, p[u].v);
+        if (flags & BNNP_F_WRITE_M) st_f4(L.M + fbase + e, m[u].v);
+    }
+
+    // ---- chunk reduction: fp32 butterfly inside the warp, fp64 across warps (fixed order)
+#pragma unroll
+    for (int k = 0; k < BNNP_NRED; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < BNNP_NRED; ++k) s_red[warp][k] = (double)acc[k];
+    }
+    __syncthreads();
+    if (tid < BNNP_NRED) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) s += s_red[w][tid];
+        L.partials[(int64_t)chunk * BNNP_NRED + tid] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t ticket = atomicAdd(L.tickets + seg, 1u);
+        s_last = (ticket == (uint32_t)(sd.num_chunks - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    // ---- segment epilogue, run by the last CTA of this segment to finish
+    __threadfence();
+    {
+        const double* base = L.partials + (int64_t)sd.first_chunk * BNNP_NRED + warp;   // warp w sums value w
+        double s = 0.0;
+        for (int ch = lane; ch < sd.num_chunks; ch += 32) s += ld_cg_f64(base + (int64_t)ch * BNNP_NRED);
+        s = warp_sum_f64(s);
+        if (lane == 0) s_red[0][warp] = s;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+
+    const double gm_old = s_red[0][R_GM_OLD], gm_new = s_red[0][R_GM_NEW];
+    const double mm_old = s_red[0][R_MM_OLD], mm_new = s_red[0][R_MM_NEW];
+    const double pg = s_red[0][R_PG], gg = s_red[0][R_GG];
+    double* st = L.seg_state + (int64_t)seg * BNNP_STATE_STRIDE;
+    const double M = sd.precond;
+    const bool metrics = flags & BNNP_F_CALC_METRICS;
+
+    st[BNNP_S_GM_OLD] = gm_old;
+    st[BNNP_S_GM_NEW] = gm_new;
+    st[BNNP_S_MM_OLD] = mm_old;
+    st[BNNP_S_MM_NEW] = mm_new;
+    if (flags & BNNP_F_READ_G) {
+        st[BNNP_S_SUM_GG] = gg;
+        st[BNNP_S_NONFINITE] = (s_red[0][R_NONFINITE] == 0.0) ? 0.0 : 1.0;
+    }
+    if (L.op == BNNP_OP_VERLET) {
+        const double c_gm = L.c_gm_base * M;                       // verlet_sgld.py:170
+        if (L.phase == BNNP_PHASE_INITIAL) {
+            st[BNNP_S_DELTA_ENERGY] = -((M * M) * L.curv_base * gg);   // :171-172 with :44-47
+        } else {
+            double de = st[BNNP_S_DELTA_ENERGY];
+            de += st[BNNP_S_PREV_NEW_MOM];                          // :174
+            de += c_gm * gm_old;                                    // :175
+            st[BNNP_S_DELTA_ENERGY] = de;
+        }
+        st[BNNP_S_PREV_NEW_MOM] = c_gm * gm_new;                    // :176
+        if (metrics) st[BNNP_S_EST_MM] = (L.phase == BNNP_PHASE_FINAL) ? mm_new : mm_old;   // :181-187
+    } else if (L.op == BNNP_OP_HMC) {
+        if (L.phase == BNNP_PHASE_INITIAL) st[BNNP_S_DELTA_ENERGY] = -0.5 * mm_old;         // hmc.py:50-53
+        if (metrics) st[BNNP_S_EST_MM] = (L.phase == BNNP_PHASE_FINAL) ? mm_new : mm_old;   // :55,60,72
+    } else if (L.op == BNNP_OP_SGLD) {
+        if (metrics) st[BNNP_S_EST_MM] = mm_old;                    // sgld.py:127,137
+    }
+    if (metrics && L.op <= BNNP_OP_HMC) st[BNNP_S_EST_PG] = pg;     // sgld.py:146
+    if (flags & BNNP_F_WRITE_M) st[BNNP_S_SUM_MM] = mm_new;
+    else if (flags & BNNP_F_READ_M) st[BNNP_S_SUM_MM] = mm_old;
+    if (flags & BNNP_F_UPDATE_SQ)                                   // sgld.py:153-154, through its mean
+        st[BNNP_S_SQ_MEAN] = L.rms_alpha * st[BNNP_S_SQ_MEAN] + (1.0 - L.rms_alpha) * (gg / (double)sd.numel);
+    if (PRIOR && (flags & BNNP_F_LOG_PRIOR))
+        st[BNNP_S_LOG_PRIOR] = s_red[0][R_LOGP] + (double)sd.numel * log_prior_const(sd);
+    st[BNNP_S_LAUNCHES] += 1.0;
+    L.tickets[seg] = 0u;   // ready for the next (stream-ordered) launch
+}
+
+// P,G,M <- prev_* : verlet_sgld.py:63-69
+__global__ void __launch_bounds__(THREADS) bnnp_rollback_kernel(float* __restrict__ P, float* __restrict__ G,
+                                                                float* __restrict__ M,
+                                                                const float* __restrict__ pp,
+                                                                const float* __restrict__ pg,
+                                                                const float* __restrict__ pm, int64_t nquads) {
+    const int64_t stride = (int64_t)gridDim.x * THREADS;
+    for (int64_t q = (int64_t)blockIdx.x * THREADS + threadIdx.x; q < nquads; q += stride) {
+        const float4 a = ld_f4(pp + 4 * q), b = ld_f4(pg + 4 * q);
+        float4 cc;
+        if (pm != nullptr) cc = ld_f4(pm + 4 * q);
+        st_f4(P + 4 * q, a);
+        st_f4(G + 4 * q, b);
+        if (pm != nullptr) st_f4(M + 4 * q, cc);
+    }
+}
+
+typedef void (*StepKernel)(const BnnpLaunch);
+
+StepKernel pick_kernel(int noise, bool prior) {
+    switch (noise) {
+        case BNNP_NOISE_NONE: return prior ? bnnp_step_kernel<BNNP_NOISE_NONE, true> : bnnp_step_kernel<BNNP_NOISE_NONE, false>;
+        case BNNP_NOISE_REPLAY: return prior ? bnnp_step_kernel<BNNP_NOISE_REPLAY, true> : bnnp_step_kernel<BNNP_NOISE_REPLAY, false>;
+        case BNNP_NOISE_PHILOX: return prior ? bnnp_step_kernel<BNNP_NOISE_PHILOX, true> : bnnp_step_kernel<BNNP_NOISE_PHILOX, false>;
+    }
+    return nullptr;
+}
+
+bool misaligned(const void* p) { return ((uintptr_t)p & 15u) != 0; }
+
+}  // namespace
+
+extern "C" {
+
+int bnnp_abi_version(void) { return BNNP_ABI_VERSION; }
+
+const char* bnnp_last_error(void) { return g_err; }
+
+int bnnp_device_info(int device, int* sm_count, int* l2_bytes) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceProperties");
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = prop.l2CacheSize;
+    return 0;
+}
+
+int bnnp_max_ctas_per_sm(int noise, int has_prior, int* out) {
+    StepKernel k = pick_kernel(noise, has_prior != 0);
+    if (k == nullptr || out == nullptr) return fail(BNNP_E_ARG, "bnnp_max_ctas_per_sm: bad noise kind");
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, THREADS, 0);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    return 0;
+}
+
+int bnnp_plan_layout(const int64_t* numel, int nseg, int64_t* off, int32_t* first_chunk, int32_t* num_chunks,
+                     int64_t* total_elems, int32_t* total_chunks, int32_t* chunk_seg) {
+    if (numel == nullptr || nseg < 0 || off == nullptr || first_chunk == nullptr || num_chunks == nullptr)
+        return fail(BNNP_E_ARG, "bnnp_plan_layout: null argument");
+    int64_t o = 0, ch = 0;
+    for (int i = 0; i < nseg; ++i) {
+        if (numel[i] <= 0) return fail(BNNP_E_ARG, "bnnp_plan_layout: segments must not be empty");
+        const int64_t nch = (numel[i] + BNNP_CHUNK - 1) / BNNP_CHUNK;
+        if (ch + nch > INT32_MAX) return fail(BNNP_E_ARG, "bnnp_plan_layout: too many chunks");
+        off[i] = o;
+        first_chunk[i] = (int32_t)ch;
+        num_chunks[i] = (int32_t)nch;
+        if (chunk_seg != nullptr)
+            for (int64_t k = 0; k < nch; ++k) chunk_seg[ch + k] = i;
+        ch += nch;
+        o += (numel[i] + BNNP_SEG_ALIGN - 1) / BNNP_SEG_ALIGN * BNNP_SEG_ALIGN;
+    }
+    if (total_elems) *total_elems = o;
+    if (total_chunks) *total_chunks = (int32_t)ch;
+    return 0;
+}
+
+int bnnp_launch(const BnnpLaunch* a, void* stream) {
+    if (a == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: null args");
+    if (a->nseg <= 0 || a->nchunks <= 0) return fail(BNNP_E_ARG, "bnnp_launch: empty chain");
+    if (a->segs == nullptr || a->chunk_seg == nullptr || a->seg_state == nullptr || a->partials == nullptr ||
+        a->tickets == nullptr)
+        return fail(BNNP_E_ARG, "bnnp_launch: null table pointer");
+    if (a->op < BNNP_OP_SGLD || a->op > BNNP_OP_REDUCE) return fail(BNNP_E_ARG, "bnnp_launch: bad op");
+    if (a->phase < BNNP_PHASE_INITIAL || a->phase > BNNP_PHASE_FINAL) return fail(BNNP_E_ARG, "bnnp_launch: bad phase");
+    const uint32_t f = a->flags;
+    if ((f & (BNNP_F_READ_P | BNNP_F_WRITE_P)) && a->P == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: P is null");
+    if ((f & BNNP_F_READ_G) && a->G == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: G is null");
+    if ((f & (BNNP_F_READ_M | BNNP_F_WRITE_M)) && a->M == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: M is null");
+    if ((f & BNNP_F_WRITE_P) && !(f & BNNP_F_READ_P)) return fail(BNNP_E_ARG, "bnnp_launch: WRITE_P needs READ_P");
+    if ((f & BNNP_F_SAVE_STATE) && (a->prev_p == nullptr || a->prev_g == nullptr))
+        return fail(BNNP_E_ARG, "bnnp_launch: SAVE_STATE needs prev_p and prev_g");
+    if (a->noise == BNNP_NOISE_REPLAY && a->replay_noise == nullptr)
+        return fail(BNNP_E_ARG, "bnnp_launch: replay noise is null");
+    if (misaligned(a->P) || misaligned(a->G) || misaligned(a->M) || misaligned(a->prev_p) || misaligned(a->prev_g) ||
+        misaligned(a->prev_m) || misaligned(a->replay_noise))
+        return fail(BNNP_E_ALIGN, "bnnp_launch: flat arrays must be 16-byte aligned");
+    const bool prior = (f & (BNNP_F_LOG_PRIOR | BNNP_F_PRIOR_GRAD)) != 0;
+    if (prior && !(f & BNNP_F_READ_P)) return fail(BNNP_E_ARG, "bnnp_launch: the prior needs READ_P");
+    StepKernel k = pick_kernel(a->noise, prior);
+    if (k == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: bad noise kind");
+    k<<<a->nchunks, THREADS, 0, (cudaStream_t)stream>>>(*a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "bnnp_step_kernel launch");
+    return 0;
+}
+
+int bnnp_rollback(float* P, float* G, float* M, const float* prev_p, const float* prev_g, const float* prev_m,
+                  int64_t total, void* stream) {
+    if (P == nullptr || G == nullptr || prev_p == nullptr || prev_g == nullptr || total <= 0)
+        return fail(BNNP_E_ARG, "bnnp_rollback: null argument");
+    if ((prev_m != nullptr) != (M != nullptr) && prev_m != nullptr)
+        return fail(BNNP_E_ARG, "bnnp_rollback: prev_m without M");
+    if (total % 4 != 0) return fail(BNNP_E_ALIGN, "bnnp_rollback: total must be a multiple of 4 floats");
+    if (misaligned(P) || misaligned(G) || misaligned(M) || misaligned(prev_p) || misaligned(prev_g) || misaligned(prev_m))
+        return fail(BNNP_E_ALIGN, "bnnp_rollback: flat arrays must be 16-byte aligned");
+    const int64_t nquads = total / 4;
+    int64_t blocks = (nquads + THREADS - 1) / THREADS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bnnp_rollback_kernel<<<(int)blocks, THREADS, 0, (cudaStream_t)stream>>>(P, G, M, prev_p, prev_g,
+                                                                              M != nullptr ? prev_m : nullptr, nquads);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "bnnp_rollback_kernel launch");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,455 @@
+"""Flat HBM storage of one Markov chain's parameter group and the launch plumbing
+around `bnnp_launch` (include/bnnp.h).
+
+The reference keeps one tensor per parameter for p, p.grad, momentum_buffer,
+square_avg, prev_* and loops over them in Python (mcmc/sgld.py:94-105).  Here a
+group owns three (six with snapshots) flat fp32 arrays; the model's parameters,
+their .grad and state['momentum_buffer'] are re-pointed to views of them, so the
+whole group is updated by one kernel launch and the reference's callers
+(runners, lr schedulers, load_state_dict) keep seeing ordinary tensors.
+
+torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _native as N
+
+# keys of optimizer.state[p] whose values live on the device between launches
+LAZY_SCALARS = ("est_temperature", "est_config_temp", "delta_energy", "prev_new_momentum_delta")
+
+
+class SegState(dict):
+    """optimizer.state[p].  A real dict (torch.optim.Optimizer expects one) whose
+    device-resident entries are filled in from the segment-state array the first
+    time somebody looks, so a step costs no host synchronisation unless a scalar
+    is actually read (SURVEY 8b "Threading / sync")."""
+
+    __slots__ = ("_fg", "_i")
+
+    def __init__(self, fg: "FlatGroup", i: int):
+        super().__init__()
+        self._fg = fg
+        self._i = i
+
+    # -- reads
+    def __getitem__(self, k):
+        if k in LAZY_SCALARS:
+            self._fg.materialize()
+        elif k == "square_avg":
+            return self._fg.square_avg_tensor(self._i)
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        try:
+            return self[k]
+        except KeyError:
+            return default
+
+    def __contains__(self, k):
+        if k in LAZY_SCALARS:
+            self._fg.materialize()
+        elif k == "square_avg":
+            return True
+        return dict.__contains__(self, k)
+
+    def _all(self):
+        self._fg.materialize()
+        return self
+
+    def keys(self):
+        return dict.keys(self._all())
+
+    def items(self):
+        return dict.items(self._all())
+
+    def values(self):
+        return dict.values(self._all())
+
+    def __iter__(self):
+        return dict.__iter__(self._all())
+
+    def __len__(self):
+        return dict.__len__(self._all())
+
+    def __repr__(self):
+        return dict.__repr__(self._all())
+
+    # -- writes
+    def __setitem__(self, k, v):
+        fg, i = self._fg, self._i
+        if k == "preconditioner":
+            v = float(v)
+            fg.set_preconditioner(i, v)
+        elif k == "momentum_buffer":
+            v = fg.set_momentum(i, v)
+        elif k == "delta_energy":
+            fg.poke(i, N.S_DELTA_ENERGY, float(v))
+            fg.have_delta = True
+        elif k == "prev_new_momentum_delta":
+            fg.poke(i, N.S_PREV_NEW_MOM, float(v))
+            fg.have_prev_new = True
+        elif k == "square_avg":
+            fg.poke(i, N.S_SQ_MEAN, float(v.double().mean()))
+            return
+        dict.__setitem__(self, k, v)
+
+    def raw_get(self, k, default=None):
+        return dict.get(self, k, default)
+
+    def raw_set(self, k, v):
+        dict.__setitem__(self, k, v)
+
+
+class FlatGroup:
+    """One param group of one chain in HBM."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], seed: int, stream_id: int):
+        self.params: List[torch.nn.Parameter] = list(params)
+        if not self.params:
+            raise ValueError("empty parameter group")
+        dev = self.params[0].device
+        for p in self.params:
+            if p.device.type != "cuda":
+                raise RuntimeError(
+                    "bnn_priors_b200 samplers run on CUDA tensors only (got a parameter on "
+                    f"{p.device}); there is no CPU implementation of this path")
+            if p.device != dev:
+                raise RuntimeError("all parameters of a group must live on one device")
+            if p.dtype != torch.float32:
+                raise RuntimeError(f"fp32 parameters only (got {p.dtype}); the kernels are fp32")
+            if p.numel() == 0:
+                raise RuntimeError("zero-sized parameters are not supported")
+        self.device = dev
+        self.lib = N.lib()
+        self.numel = [int(p.numel()) for p in self.params]
+        self.nseg = len(self.params)
+        off, first, nch, total, chunk_seg = N.plan_layout(self.numel)
+        self.off = [int(o) for o in off]
+        self.total = total
+        self.nchunks = int(chunk_seg.size)
+        self.n_params = int(sum(self.numel))
+
+        # segment table (host copy + device copy)
+        self.table = np.zeros(self.nseg, dtype=N.SEGMENT_DTYPE)
+        self.table["off"], self.table["numel"] = off, self.numel
+        self.table["precond"] = 1.0
+        self.table["prior_scale"], self.table["prior_df"] = 1.0, 3.0
+        self.table["first_chunk"], self.table["num_chunks"] = first, nch
+        self.table_dev = torch.empty(self.table.nbytes, dtype=torch.uint8, device=dev)
+        self._table_dirty = True
+        self.chunk_seg_dev = torch.from_numpy(np.ascontiguousarray(chunk_seg)).to(dev)
+        self._all_chunks = (self.chunk_seg_dev, self.nchunks)
+
+        # flat arrays
+        self.P = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.G = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.M: Optional[torch.Tensor] = None
+        self.prev_p = self.prev_g = self.prev_m = None
+        self.p_views = [self.P[o:o + n].view(p.shape) for o, n, p in zip(self.off, self.numel, self.params)]
+        self.g_views = [self.G[o:o + n].view(p.shape) for o, n, p in zip(self.off, self.numel, self.params)]
+        self.m_views: Optional[List[torch.Tensor]] = None
+        self._p_ptrs = [v.data_ptr() for v in self.p_views]
+
+        # per-segment scalars (BNNP_S_*) on the device, mirrored on demand
+        self.state_dev = torch.zeros(self.nseg, N.STATE_STRIDE, dtype=torch.float64, device=dev)
+        self.state_dev[:, N.S_SQ_MEAN] = 1.0          # square_avg = ones (sgld.py:170)
+        self.state_host = torch.zeros(self.nseg, N.STATE_STRIDE, dtype=torch.float64).pin_memory()
+        self.state_host[:, N.S_SQ_MEAN] = 1.0
+        self.state_np = self.state_host.numpy()
+        self.partials = torch.empty(self.nchunks * N.NRED, dtype=torch.float64, device=dev)
+        self.tickets = torch.zeros(self.nseg, dtype=torch.int32, device=dev)
+        self._epoch = 0          # bumped by every launch / poke
+        self._host_epoch = 0     # epoch state_host corresponds to
+        self._mat_epoch = 0      # epoch the SegState dicts correspond to
+        self.have_metrics = self.have_delta = self.have_prev_new = False
+        self.metrics_num_data = 1.0
+
+        # noise
+        self.key = N.philox_key(seed, stream_id)
+        self.call = 0
+        self.replay: Optional[torch.Tensor] = None
+
+        # fused prior (prior_fusion.py)
+        self.prior_fused = False
+        self.grad_max: Optional[float] = None
+        self._lp_valid = False
+        self._lp_pversion = None
+        # validity of SUM_GG / SUM_MM in the segment state
+        self._gg_version = None
+        self._mm_version = None
+
+        self.seg_states = [SegState(self, i) for i in range(self.nseg)]
+        self.args = N.BnnpLaunch()
+        self.launches = 0
+
+        self.adopt_parameters()
+
+    # ------------------------------------------------------------------ views
+    @torch.no_grad()
+    def adopt_parameters(self) -> None:
+        """Move every parameter's storage into the flat P array (in place for the
+        model: `p.data` becomes a view)."""
+        for i, (p, v) in enumerate(zip(self.params, self.p_views)):
+            v.copy_(p.data)
+            p.data = v
+            if p.grad is not None and p.grad is not self.g_views[i]:
+                self.g_views[i].copy_(p.grad)
+                p.grad = self.g_views[i]
+
+    @torch.no_grad()
+    def sync_views(self, raise_on_no_grad: bool) -> List[int]:
+        """Make sure p, p.grad (and momentum_buffer) are still the flat views; copy
+        foreign tensors in if somebody re-bound them (closures that set
+        `p.grad = None`, `Prior.sample()`).  Returns the indices of parameters that
+        have no gradient (sgld.py:96-101)."""
+        missing: List[int] = []
+        gv, pv, ptrs = self.g_views, self.p_views, self._p_ptrs
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is None:
+                if raise_on_no_grad:
+                    raise RuntimeError(f"No gradient for parameter with shape {p.shape}")
+                missing.append(i)
+            elif g is not gv[i]:
+                gv[i].copy_(g)
+                p.grad = gv[i]
+            if p.data_ptr() != ptrs[i]:
+                pv[i].copy_(p.data)
+                p.data = pv[i]
+                self._lp_valid = False
+        return missing
+
+    def ensure_momentum_storage(self) -> None:
+        if self.M is None:
+            self.M = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+            self.m_views = [self.M[o:o + n].view(p.shape) for o, n, p in zip(self.off, self.numel, self.params)]
+
+    def set_momentum(self, i: int, value: torch.Tensor) -> torch.Tensor:
+        """state['momentum_buffer'] = tensor: the values are copied into the flat M."""
+        self.ensure_momentum_storage()
+        v = self.m_views[i]
+        if value is not v:
+            with torch.no_grad():
+                v.copy_(value)
+        self._mm_version = None
+        return v
+
+    def check_momentum(self) -> None:
+        """sgld.py:107-111: stepping without sample_momentum is an error."""
+        if self.M is None or any(s.raw_get("momentum_buffer") is None for s in self.seg_states):
+            raise RuntimeError("No 'momentum_buffer' stored in state. "
+                               "Perhaps you forgot to call `sample_momentum`?")
+
+    def publish_momentum(self) -> None:
+        for s, v in zip(self.seg_states, self.m_views):
+            if s.raw_get("momentum_buffer") is not v:
+                s.raw_set("momentum_buffer", v)
+
+    def ensure_prev_storage(self, with_momentum: bool) -> None:
+        if self.prev_p is None:
+            self.prev_p = torch.zeros_like(self.P)
+            self.prev_g = torch.zeros_like(self.P)
+            for s, o, n, p in zip(self.seg_states, self.off, self.numel, self.params):
+                s.raw_set("prev_parameter", self.prev_p[o:o + n].view(p.shape))
+                s.raw_set("prev_grad", self.prev_g[o:o + n].view(p.shape))
+        if with_momentum and self.prev_m is None:
+            self.prev_m = torch.zeros_like(self.P)
+            for s, o, n, p in zip(self.seg_states, self.off, self.numel, self.params):
+                s.raw_set("prev_momentum_buffer", self.prev_m[o:o + n].view(p.shape))
+
+    def pack(self, tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Per-tensor values -> one flat array in this group's layout (replay noise)."""
+        flat = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        assert len(tensors) == self.nseg
+        for t, o, n in zip(tensors, self.off, self.numel):
+            flat[o:o + n].copy_(torch.as_tensor(t, dtype=torch.float32).reshape(-1))
+        return flat
+
+    def unpack(self, flat: torch.Tensor) -> torch.Tensor:
+        """Flat layout -> the concatenation of the tensors without padding."""
+        return torch.cat([flat[o:o + n] for o, n in zip(self.off, self.numel)])
+
+    # ------------------------------------------------------------ segment table
+    def set_preconditioner(self, i: int, v: float) -> None:
+        if self.table["precond"][i] != v:
+            self.table["precond"][i] = v
+            self._table_dirty = True
+
+    def set_prior(self, i: int, kind: int, loc: float, scale: float, df: float) -> None:
+        t = self.table
+        t["prior_kind"][i], t["prior_loc"][i], t["prior_scale"][i], t["prior_df"][i] = kind, loc, scale, df
+        self._table_dirty = True
+        self._lp_valid = False
+
+    def _upload_table(self) -> None:
+        # rare (preconditioner / prior changes): a plain blocking copy of a few KB
+        self.table_dev.copy_(torch.from_numpy(self.table.view(np.uint8).copy()))
+        self._table_dirty = False
+
+    # ------------------------------------------------------------ scalars
+    def poke(self, i: int, col: int, v: float) -> None:
+        self.state_dev[i, col] = v
+        self._epoch += 1
+
+    def fetch(self) -> np.ndarray:
+        """Host mirror of the segment-state array (one D2H copy + one stream sync,
+        only if a launch happened since the last fetch)."""
+        if self._host_epoch != self._epoch:
+            self.state_host.copy_(self.state_dev, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._host_epoch = self._epoch
+        return self.state_np
+
+    def materialize(self) -> None:
+        if self._mat_epoch == self._epoch:
+            return
+        st = self.fetch()
+        nd = self.metrics_num_data
+        for i, s in enumerate(self.seg_states):
+            d = self.numel[i]
+            if self.have_metrics:
+                s.raw_set("est_temperature", float(st[i, N.S_EST_MM]) / d)
+                s.raw_set("est_config_temp", float(st[i, N.S_EST_PG]) * (nd / d))
+            if self.have_delta:
+                s.raw_set("delta_energy", float(st[i, N.S_DELTA_ENERGY]))
+            if self.have_prev_new:
+                s.raw_set("prev_new_momentum_delta", float(st[i, N.S_PREV_NEW_MOM]))
+        self._mat_epoch = self._epoch
+
+    def square_avg_tensor(self, i: int) -> torch.Tensor:
+        """state['square_avg'] is only ever consumed through its mean
+        (sgld.py:154,173); the engine keeps that mean.  A reader gets a constant
+        tensor with the right mean."""
+        return torch.full_like(self.params[i], float(self.fetch()[i, N.S_SQ_MEAN]))
+
+    # ------------------------------------------------------------ launches
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def launch(self, op: int, phase: int, flags: int, noise: int, cm=0.0, cg=0.0, cn=0.0, cp=0.0,
+               inv_num_data=0.0, c_gm_base=0.0, curv_base=0.0, rms_alpha=0.0,
+               chunks=None) -> None:
+        if self._table_dirty:
+            self._upload_table()
+        a = self.args
+        chunk_seg, nchunks = chunks if chunks is not None else self._all_chunks
+        a.P, a.G = self.P.data_ptr(), self.G.data_ptr()
+        a.M = self.M.data_ptr() if self.M is not None else None
+        a.prev_p = self.prev_p.data_ptr() if self.prev_p is not None else None
+        a.prev_g = self.prev_g.data_ptr() if self.prev_g is not None else None
+        a.prev_m = self.prev_m.data_ptr() if (self.prev_m is not None and (flags & N.F_READ_M)) else None
+        if noise == N.NOISE_REPLAY:
+            if self.replay is None:
+                raise RuntimeError("replay noise requested but none was provided")
+            a.replay_noise = self.replay.data_ptr()
+        else:
+            a.replay_noise = None
+        a.segs, a.chunk_seg = self.table_dev.data_ptr(), chunk_seg.data_ptr()
+        a.seg_state, a.partials, a.tickets = self.state_dev.data_ptr(), self.partials.data_ptr(), self.tickets.data_ptr()
+        a.nseg, a.nchunks = self.nseg, nchunks
+        a.op, a.phase, a.noise, a.flags = op, phase, noise, flags
+        a.key0, a.key1, a.call = self.key[0], self.key[1], self.call
+        a.cm, a.cg, a.cn, a.cp = cm, cg, cn, cp
+        a.inv_num_data = inv_num_data
+        a.grad_max = self.grad_max if self.grad_max is not None else 0.0
+        a.c_gm_base, a.curv_base, a.rms_alpha = c_gm_base, curv_base, rms_alpha
+        if torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                rc = self.lib.bnnp_launch(C.byref(a), self._stream())
+        else:
+            rc = self.lib.bnnp_launch(C.byref(a), self._stream())
+        N.check(rc, "bnnp_launch")
+        self.call += 1
+        self._epoch += 1
+        self.launches += 1
+
+    def relaunch(self) -> None:
+        """Launch again with the argument block of the previous launch (same
+        coefficients, next Philox counter): the C-ABI-level hot loop that bench.py
+        times for the device-resident number."""
+        a = self.args
+        a.call = self.call
+        N.check(self.lib.bnnp_launch(C.byref(a), self._stream()), "bnnp_launch")
+        self.call += 1
+        self._epoch += 1
+        self.launches += 1
+
+    def chunks_without(self, missing: Sequence[int]):
+        """Chunk list that skips the segments in `missing` (raise_on_no_grad=False)."""
+        keep = np.ones(self.nseg, dtype=bool)
+        keep[list(missing)] = False
+        cs = self._all_chunks[0].cpu().numpy()
+        sel = np.ascontiguousarray(cs[keep[cs]])
+        if sel.size == 0:
+            return None
+        return torch.from_numpy(sel).to(self.device), int(sel.size)
+
+    def take_noise_mode(self, needs_noise: bool) -> int:
+        if not needs_noise:
+            return N.NOISE_NONE
+        return N.NOISE_REPLAY if self.replay is not None else N.NOISE_PHILOX
+
+    # ------------------------------------------------------------ reductions on demand
+    def _p_version(self) -> int:
+        return sum(p._version for p in self.params)
+
+    def note_step_sums(self, lp_computed: bool) -> None:
+        """Called after a step launch: SUM_GG / SUM_MM in the segment state now
+        describe G (the gradient the step used) and M as stored; LOG_PRIOR describes
+        P as stored if the launch carried BNNP_F_LOG_PRIOR."""
+        self._gg_version = self.G._version
+        self._mm_version = self.M._version if self.M is not None else None
+        if lp_computed:
+            self._lp_valid = True
+            self._lp_pversion = self._p_version()
+
+    def invalidate_sums(self) -> None:
+        self._gg_version = self._mm_version = None
+        self._lp_valid = False
+
+    def reduce_now(self, inv_num_data: float) -> None:
+        """dot(g,g), dot(m,m) and the log-prior of the CURRENT arrays (no writes)."""
+        flags = N.F_READ_G
+        if self.M is not None:
+            flags |= N.F_READ_M
+        if self.prior_fused:
+            flags |= N.F_READ_P | N.F_PRIOR_GRAD | N.F_LOG_PRIOR
+            if self.grad_max is not None:
+                flags |= N.F_CLAMP_GRAD
+        self.launch(N.OP_REDUCE, N.PHASE_MID, flags, N.NOISE_NONE, cm=1.0, inv_num_data=inv_num_data)
+        self._gg_version = self.G._version
+        self._mm_version = self.M._version if self.M is not None else None
+        if self.prior_fused:
+            self._lp_valid = True
+            self._lp_pversion = self._p_version()
+
+    def sums_fresh(self, need_mm: bool) -> bool:
+        if self._gg_version is None or self._gg_version != self.G._version:
+            return False
+        if need_mm and (self.M is None or self._mm_version != self.M._version):
+            return False
+        return True
+
+    def log_prior_fresh(self) -> bool:
+        return self._lp_valid and self._lp_pversion == self._p_version()
+
+    @torch.no_grad()
+    def rollback(self) -> None:
+        """verlet_sgld.py:63-69 on the flat arrays."""
+        if self.prev_p is None:
+            raise KeyError("prev_parameter")
+        pm = self.prev_m if (self.prev_m is not None and self.M is not None) else None
+        rc = self.lib.bnnp_rollback(self.P.data_ptr(), self.G.data_ptr(),
+                                    self.M.data_ptr() if pm is not None else None,
+                                    self.prev_p.data_ptr(), self.prev_g.data_ptr(),
+                                    pm.data_ptr() if pm is not None else None,
+                                    self.total, self._stream())
+        N.check(rc, "bnnp_rollback")
+        self.launches += 1
+        self.invalidate_sums()

@@ -1,0 +1,77 @@
+"""HMC with Verlet (leapfrog) integration.
+
+Mirror of the reference's `bnn_priors/mcmc/hmc.py` (class `HMC`, :10-79): really
+`VerletSGLD` with momentum=1 and temperature=1, no noise inside a trajectory, and
+the kinetic energy 1/2 m.m as the point energy of the M-H acceptance probability.
+The user calls `sample_momentum` to refresh the momentum between trajectories.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Union
+
+import torch
+
+from .. import _native as N
+from ._flat import FlatGroup
+from .sgld import dot  # noqa: F401
+from .verlet_sgld import VerletSGLD
+
+
+class HMC(VerletSGLD):
+    """HMC with Verlet integration.
+
+    Args (identical to the reference, mcmc/hmc.py:25-27):
+        params (iterable): iterable of parameters to optimize or dicts defining
+            parameter groups
+        lr (float): learning rate
+        num_data (int): the number of data points in this learning task
+        raise_on_no_grad (bool): whether to complain if a parameter does not
+                                 have a gradient
+        raise_on_nan: whether to complain if a gradient is not all finite.
+    """
+    _OP = N.OP_HMC
+
+    def __init__(self, params: Sequence[Union[torch.nn.Parameter, Dict]],
+                 lr: float, num_data: int,
+                 raise_on_no_grad: bool = True, raise_on_nan: bool = True,
+                 *, seed: Optional[int] = None, chain: int = 0):
+        super().__init__(params, lr, num_data, 1., 1.,
+                         raise_on_no_grad=raise_on_no_grad,
+                         raise_on_nan=raise_on_nan, seed=seed, chain=chain)
+
+    def _point_energy_i(self, group, fg: FlatGroup, i: int) -> float:
+        "hmc.py:32-33: .5 * dot(momentum, momentum) of the momentum now stored"
+        return .5 * float(fg.fetch()[i, N.S_SUM_MM])
+
+    def _update_group_fn(self, g):
+        # Ensure momentum and temperature are correct at every step
+        # No matter what modifications are done before `self.step`.
+        super()._update_group_fn(g)
+        assert g['momentum'] == 1. and g['temperature'] == 1.
+
+    def _step_fn(self, group, fg: FlatGroup, chunks, is_initial=False, is_final=False,
+                 save_state=False, calc_metrics=True):
+        """One leapfrog transition of a whole group (mcmc/hmc.py:41-79):
+        m += grad_lr*g  (grad_v = 1 / 2 / 1 for initial / intermediate / final);
+        p += bh*M*m unless final.  No noise."""
+        fg.check_momentum()
+        pf, inv_n = self._prior_flags(fg, group)
+        flags = N.F_READ_P | N.F_READ_G | N.F_READ_M | N.F_WRITE_M | pf
+        if calc_metrics:
+            flags |= N.F_CALC_METRICS
+        if save_state:
+            fg.ensure_prev_storage(with_momentum=True)
+            flags |= N.F_SAVE_STATE
+        if not is_final:
+            flags |= N.F_WRITE_P | N.F_UPDATE_SQ
+            if pf:
+                flags |= N.F_LOG_PRIOR
+        fg.launch(self._OP, self._phase(is_initial, is_final), flags, N.NOISE_NONE,
+                  cm=1.0, cg=-.5 * group['grad_v'] * group['bhn'], cn=0.0, cp=group['bh'],
+                  inv_num_data=inv_n, rms_alpha=group['rmsprop_alpha'], chunks=chunks)
+        if calc_metrics:
+            fg.have_metrics = True
+            fg.metrics_num_data = group['num_data']
+        if is_initial:
+            fg.have_delta = True
+        fg.note_step_sums(bool(pf) and not is_final)

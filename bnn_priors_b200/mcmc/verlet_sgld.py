@@ -1,0 +1,196 @@
+"""GGMC / OBABO ("VerletSGLD") with Metropolis-Hastings correction.
+
+Mirror of the reference's `bnn_priors/mcmc/verlet_sgld.py` (class `VerletSGLD`,
+:8-197).  The initial / intermediate / final transitions, the snapshot for
+rejection, the per-tensor delta-energy bookkeeping and the temperature diagnostics
+are all done by one kernel launch per transition (csrc/bnnp_kernels.cu); the
+accept/reject decision stays on the host, with the uniform drawn from the CPU
+generator exactly as the reference does (verlet_sgld.py:61).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import torch
+
+from .. import _native as N
+from ._flat import FlatGroup
+from .sgld import SGLD, dot  # noqa: F401  (dot re-exported like the reference)
+
+
+class VerletSGLD(SGLD):
+    """SGLD with momentum, preconditioning and diagnostics from Wenzel et al. 2020.
+    Uses Verlet integration instead of Euler symplectic integration.
+
+    The contribution from the Verlet integration to the acceptance probability
+    is neutral (multiply by 1), because it is perfectly time-reversible.
+
+    Args: see `SGLD` (the reference's signature, mcmc/sgld.py:31-34).
+    """
+    _OP = N.OP_VERLET
+
+    # ------------------------------------------------------------------ energies
+    def _group_of(self, p):
+        for group, fg in zip(self.param_groups, self._flat):
+            for i, q in enumerate(fg.params):
+                if q is p:
+                    return group, fg, i
+        raise KeyError("parameter is not managed by this sampler")
+
+    def _refresh_sums(self, group, fg: FlatGroup):
+        """Make SUM_GG (and SUM_MM) in the segment state describe the current
+        p.grad / momentum: free right after a step, one read-only launch if
+        somebody changed them since."""
+        if not fg.sums_fresh(need_mm=self._OP == N.OP_HMC):
+            fg.sync_views(raise_on_no_grad=True)
+            fg.reduce_now(1.0 / group['num_data'] if fg.prior_fused else 0.0)
+
+    def delta_energy(self, prev_potential: float, potential: float) -> float:
+        "Calculates the difference in energy since the last `initial_step` and now."
+        num_data = self.param_groups[0]['num_data']
+        assert all(g['num_data'] == num_data for g in self.param_groups),\
+            "unclear which `num_data` to use"
+        delta_energy = 0.
+        for group, fg in zip(self.param_groups, self._flat):
+            self._refresh_sums(group, fg)
+            if not fg.have_delta:
+                raise KeyError('delta_energy')
+            st = fg.fetch()
+            for i, p in enumerate(fg.params):
+                point_energy = self._point_energy_i(group, fg, i)
+                delta_energy += float(st[i, N.S_DELTA_ENERGY]) + point_energy
+
+        if isinstance(potential, torch.Tensor):
+            potential = potential.item()
+        delta_energy += (potential - prev_potential) * num_data
+        return delta_energy
+
+    def _point_energy_i(self, group, fg: FlatGroup, i: int) -> float:
+        M_rsqrt = float(fg.table["precond"][i])
+        curv = M_rsqrt**2 * group['num_data']**2 * group['b^2h^2'] / 8
+        return curv * float(fg.fetch()[i, N.S_SUM_GG])
+
+    def _point_energy(self, group, p, state):
+        "verlet_sgld.py:44-47; dot(p.grad, p.grad) comes from the kernel's reduction"
+        _, fg, i = self._group_of(p)
+        self._refresh_sums(group, fg)
+        return self._point_energy_i(group, fg, i)
+
+    @torch.no_grad()
+    def maybe_reject(self, delta_energy: float) -> (bool, float):
+        "Maybe reject the current parameters, based on the difference in energy"
+        temperature = self.param_groups[0]['temperature']
+        assert all(g['temperature'] == temperature for g in self.param_groups),\
+            "unclear which `temperature` to use"
+
+        if temperature == 0.0:
+            return False, 0.  # Never reject
+
+        # rand() > min(1., exp(-delta_energy / temperature))
+        log_accept_prob = -delta_energy / temperature
+        reject = (math.log(torch.rand(()).item()) > log_accept_prob)
+        if reject:
+            for fg in self._flat:
+                fg.sync_views(raise_on_no_grad=False)
+                fg.rollback()
+        return reject, log_accept_prob
+
+    # ------------------------------------------------------------------ transitions
+    @torch.no_grad()
+    def initial_step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
+                     save_state=True, calc_metrics=True):
+        """The initial transition for the Verlet integrator.
+        θ(n), m(n) -> θ(n+1), u(n+1)
+
+        u(n) is not the momentum, rather, it is
+        u(n) = sqrt(b)*m(n) - gradient of parameters
+        """
+        # keep a `torch.optim.lr_scheduler` happy
+        self._step_count = getattr(self, '_step_count', 0) + 1
+
+        def update_group_fn(g):
+            self._update_group_fn(g)
+            a = g['momentum']
+            g['mom_decay'] = math.sqrt(a)
+            g['grad_v'] = 1.
+            g['noise_std'] = math.sqrt((1 - a) * g['temperature'])
+        return self._step_internal(update_group_fn, self._step_fn, closure,
+                                   is_initial=True, save_state=save_state,
+                                   calc_metrics=calc_metrics)
+
+    @torch.no_grad()
+    def step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
+             calc_metrics=True):
+        """An intermediate transition for the Verlet integrator.
+        θ(n), u(n) -> θ(n+1), u(n+1)
+        """
+        return self._step_internal(self._update_group_fn, self._step_fn,
+                                   closure, calc_metrics=calc_metrics)
+
+    @torch.no_grad()
+    def final_step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
+                   calc_metrics=True):
+        """The final transition for the Verlet integrator
+        θ(n), u(n) -> θ(n), m(n)
+        """
+        # keep a `torch.optim.lr_scheduler` happy
+        self._step_count = getattr(self, '_step_count', 0) + 1
+
+        def update_group_fn(g):
+            self._update_group_fn(g)
+            a = g['momentum']
+            g['mom_decay'] = math.sqrt(a)
+            g['grad_v'] = g['mom_decay']
+            g['noise_std'] = math.sqrt((1 - a) * g['temperature'])
+        return self._step_internal(update_group_fn, self._step_fn, closure,
+                                   is_final=True, calc_metrics=calc_metrics)
+
+    def _update_group_fn(self, g):
+        g['b^2h^2'] = g['lr'] / g['num_data']
+        g['bh'] = math.sqrt(g['b^2h^2'])
+        g['bhn'] = math.sqrt(g['lr'] * g['num_data'])
+
+        a = g['momentum']
+        g['mom_decay'] = a
+        g['grad_v'] = 1 + a
+        g['noise_std'] = math.sqrt((1 - a**2) * g['temperature'])
+
+    def _phase(self, is_initial, is_final):
+        return N.PHASE_INITIAL if is_initial else (N.PHASE_FINAL if is_final else N.PHASE_MID)
+
+    def _step_fn(self, group, fg: FlatGroup, chunks, is_initial=False, is_final=False,
+                 save_state=False, calc_metrics=True):
+        """One GGMC transition of a whole group (mcmc/verlet_sgld.py:149-197):
+        m' = noise_std*eps + grad_lr*g + mom_decay*m ;  p += bh*M*m' (unless final)."""
+        fg.check_momentum()
+        pf, inv_n = self._prior_flags(fg, group)
+        flags = N.F_READ_P | N.F_READ_G | N.F_READ_M | N.F_WRITE_M | N.F_NOISE_FIRST | pf
+        if calc_metrics:
+            flags |= N.F_CALC_METRICS
+        if save_state:
+            fg.ensure_prev_storage(with_momentum=group['momentum'] > 0)
+            flags |= N.F_SAVE_STATE
+        if not is_final:
+            flags |= N.F_WRITE_P | N.F_UPDATE_SQ
+            if pf:
+                flags |= N.F_LOG_PRIOR
+        # the reference draws randn_like(p) even when noise_std == 0 (:163); a replayed
+        # trace carries that draw, the Philox stream simply skips it
+        noise = fg.take_noise_mode(True)
+        if noise == N.NOISE_PHILOX and group['noise_std'] == 0.0:
+            noise = N.NOISE_NONE
+        bhn = group['bhn']
+        fg.launch(self._OP, self._phase(is_initial, is_final), flags, noise,
+                  cm=group['mom_decay'], cg=-.5 * group['grad_v'] * bhn, cn=group['noise_std'],
+                  cp=group['bh'], inv_num_data=inv_n, c_gm_base=-.5 * bhn,
+                  curv_base=group['num_data']**2 * group['b^2h^2'] / 8,
+                  rms_alpha=group['rmsprop_alpha'], chunks=chunks)
+        self._consume_replay(fg)
+        if calc_metrics:
+            fg.have_metrics = True
+            fg.metrics_num_data = group['num_data']
+        fg.have_prev_new = True
+        if is_initial:
+            fg.have_delta = True
+        fg.note_step_sums(bool(pf) and not is_final)

@@ -1,0 +1,179 @@
+/* bnnp.h -- C ABI of the B200 (sm_100a) SG-MCMC sampler kernels.
+ *
+ * This is the drop-in boundary for ONE path of ratschlab/bnn_priors: the inner
+ * loop of bnn_priors/mcmc (SGLD, VerletSGLD, HMC) plus the elementwise
+ * Normal / Laplace / Student-t prior gradient.  Each entry point names the
+ * reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - plain C types only; every pointer inside BnnpLaunch is a DEVICE pointer
+ *    owned by the caller; the library never allocates, frees or synchronises.
+ *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered.
+ *  - return value 0 = success, negative = BNNP_E_* (bad argument), positive = a
+ *    cudaError_t; bnnp_last_error() gives the text (thread-local).
+ *  - no exceptions cross this boundary.
+ *
+ * Data layout (DESIGN.md "Layout in HBM").  One chain = flat fp32 arrays
+ * P, G, M (parameters, p.grad, momentum_buffer) of `total` floats, optional
+ * PREV_P, PREV_G, PREV_M (verlet_sgld.py:72-83 snapshots) and an optional
+ * replay-noise array, all with the SAME layout: tensor t (a "segment") occupies
+ * [off_t, off_t + numel_t), off_t a multiple of BNNP_SEG_ALIGN floats; the gap
+ * up to the next segment is padding the kernels keep at zero.  A segment is cut
+ * into chunks of BNNP_CHUNK floats; one CTA processes one chunk.
+ */
+#ifndef BNNP_H
+#define BNNP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNNP_ABI_VERSION 2
+
+#define BNNP_SEG_ALIGN 32      /* floats: every segment starts on a 128-byte line */
+#define BNNP_THREADS 256       /* threads per CTA                                 */
+#define BNNP_UNROLL 4          /* 128-bit accesses per thread per stream          */
+#define BNNP_CHUNK (BNNP_THREADS * BNNP_UNROLL * 4)   /* 4096 floats per CTA      */
+
+#define BNNP_NRED 8            /* partial sums per chunk                          */
+#define BNNP_STATE_STRIDE 16   /* doubles per segment in seg_state                */
+
+enum { BNNP_E_ARG = -1, BNNP_E_ALIGN = -2, BNNP_E_UNSUPPORTED = -3 };
+
+/* prior kinds (reference: prior/loc_scale.py:34-35 Normal, :66-67 Laplace,
+ * :74-77 StudentT; NONE = the prior gradient is already inside G) */
+enum { BNNP_PRIOR_NONE = 0, BNNP_PRIOR_NORMAL = 1, BNNP_PRIOR_LAPLACE = 2, BNNP_PRIOR_STUDENT_T = 3 };
+
+/* which sampler's bookkeeping the per-segment epilogue applies */
+enum {
+    BNNP_OP_SGLD = 0,            /* mcmc/sgld.py:119-154                          */
+    BNNP_OP_VERLET = 1,          /* mcmc/verlet_sgld.py:149-197                   */
+    BNNP_OP_HMC = 2,             /* mcmc/hmc.py:41-79                             */
+    BNNP_OP_SAMPLE_MOMENTUM = 3, /* mcmc/sgld.py:57-69                            */
+    BNNP_OP_REDUCE = 4           /* dot(g,g), dot(m,m), sum log-prior; no writes:
+                                    sgld.py:9-11, verlet_sgld.py:44-47, hmc.py:32-33,
+                                    models/base.py:25-30                          */
+};
+enum { BNNP_PHASE_INITIAL = 0, BNNP_PHASE_MID = 1, BNNP_PHASE_FINAL = 2 };
+
+/* BnnpLaunch.flags */
+enum {
+    BNNP_F_READ_P = 1u << 0,
+    BNNP_F_READ_G = 1u << 1,
+    BNNP_F_READ_M = 1u << 2,
+    BNNP_F_WRITE_P = 1u << 3,       /* p += (cp*M) * m'                              */
+    BNNP_F_WRITE_M = 1u << 4,       /* momentum_buffer <- m'                         */
+    BNNP_F_SAVE_STATE = 1u << 5,    /* verlet_sgld.py:72-83 fused into the step      */
+    BNNP_F_CALC_METRICS = 1u << 6,  /* est_temperature / est_config_temp             */
+    BNNP_F_LOG_PRIOR = 1u << 7,     /* also reduce sum log p(theta) at the theta left
+                                       in P by this launch                           */
+    BNNP_F_CLAMP_GRAD = 1u << 8,    /* inference.py:219-220 re-applied to g + prior  */
+    BNNP_F_NOISE_FIRST = 1u << 9,   /* m' = (cn*eps + cg*M*g) + cm*m, the rounding
+                                       order of verlet_sgld.py:163-167; otherwise
+                                       m' = (cm*m + cg*M*g) + cn*eps, sgld.py:129,142 */
+    BNNP_F_MM_PRE_NOISE = 1u << 10, /* sgld.py:132-137 (momentum == 0): the metric is
+                                       dot(m', m') before the noise is added         */
+    BNNP_F_UPDATE_SQ = 1u << 11,    /* square_avg moving average, sgld.py:153-154    */
+    BNNP_F_PRIOR_GRAD = 1u << 12    /* g <- g - (1/N) dlog p/dtheta in-register: models/
+                                       base.py:72-77 + inference.py:218 without autograd */
+};
+
+/* noise source */
+enum { BNNP_NOISE_NONE = 0, BNNP_NOISE_REPLAY = 1, BNNP_NOISE_PHILOX = 2 };
+
+/* indices into one segment's BNNP_STATE_STRIDE doubles */
+enum {
+    BNNP_S_DELTA_ENERGY = 0,   /* state['delta_energy']                       */
+    BNNP_S_PREV_NEW_MOM = 1,   /* state['prev_new_momentum_delta']            */
+    BNNP_S_EST_MM = 2,         /* numerator of state['est_temperature']       */
+    BNNP_S_EST_PG = 3,         /* dot(p, grad) of state['est_config_temp']    */
+    BNNP_S_SUM_GG = 4,         /* dot(grad, grad) seen by the last launch     */
+    BNNP_S_SUM_MM = 5,         /* dot(m, m) of the momentum now in M          */
+    BNNP_S_SQ_MEAN = 6,        /* mean(state['square_avg'])                   */
+    BNNP_S_LOG_PRIOR = 7,      /* sum log p(theta)  (BNNP_F_LOG_PRIOR)        */
+    BNNP_S_GM_OLD = 8,         /* raw sums of the last launch ...             */
+    BNNP_S_GM_NEW = 9,
+    BNNP_S_MM_OLD = 10,
+    BNNP_S_MM_NEW = 11,
+    BNNP_S_NONFINITE = 12,     /* 1.0 if the gradient had a non-finite entry  */
+    BNNP_S_LAUNCHES = 13       /* number of launches that finalised this segment */
+};
+
+/* One parameter tensor.  A table of these lives in device memory. */
+typedef struct BnnpSegment {
+    int64_t off;         /* element offset in the flat layout (multiple of
+                            BNNP_SEG_ALIGN)                                     */
+    int64_t numel;       /* > 0                                                */
+    double precond;      /* state['preconditioner'] (sgld.py:47-52)            */
+    float prior_loc, prior_scale, prior_df;
+    int32_t prior_kind;
+    int32_t first_chunk; /* index of this segment's first chunk                */
+    int32_t num_chunks;  /* ceil(numel / BNNP_CHUNK)                           */
+} BnnpSegment;
+
+typedef struct BnnpLaunch {
+    float* P;                  /* flat [total]                                      */
+    float* G;
+    float* M;
+    float* prev_p;             /* flat [total] or null (BNNP_F_SAVE_STATE)          */
+    float* prev_g;
+    float* prev_m;
+    const float* replay_noise; /* flat [total], BNNP_NOISE_REPLAY                   */
+    const BnnpSegment* segs;   /* [nseg]                                            */
+    const int32_t* chunk_seg;  /* [nchunks]: segment of every chunk                 */
+    double* seg_state;         /* [nseg][BNNP_STATE_STRIDE]                         */
+    double* partials;          /* scratch [nchunks][BNNP_NRED]                      */
+    uint32_t* tickets;         /* [nseg], zero-initialised once                     */
+    int32_t nseg, nchunks;
+    int32_t op, phase, noise;
+    uint32_t flags;
+    uint32_t key0, key1;       /* Philox key                                        */
+    uint64_t call;             /* Philox counter words 2,3: one value per launch    */
+    /* m' from cm*m, (cg*M)*g, cn*eps ;  p' = p + (cp*M)*m'   (M = precond)         */
+    double cm, cg, cn, cp;
+    double inv_num_data;       /* 1/N for the fused prior gradient                  */
+    double grad_max;           /* BNNP_F_CLAMP_GRAD                                 */
+    double c_gm_base;          /* -bhn/2        (verlet_sgld.py:170)                */
+    double curv_base;          /* N^2 b^2h^2/8  (verlet_sgld.py:46)                 */
+    double rms_alpha;          /* sgld.py:153                                       */
+} BnnpLaunch;
+
+int bnnp_abi_version(void);
+const char* bnnp_last_error(void);
+
+/* SM count and L2 size of a device (grid sizing, bench bookkeeping). */
+int bnnp_device_info(int device, int* sm_count, int* l2_bytes);
+/* Resident CTAs per SM of the step-kernel instantiation (noise, has_prior). */
+int bnnp_max_ctas_per_sm(int noise, int has_prior, int* out);
+
+/* Host helper (no GPU needed): flat-layout offsets and chunk table for `nseg`
+ * tensors.  Fills off[nseg], first_chunk[nseg], num_chunks[nseg]; returns the
+ * totals.  chunk_seg may be null; otherwise it must hold *total_chunks ints
+ * (call once with null to size it). */
+int bnnp_plan_layout(const int64_t* numel, int nseg,
+                     int64_t* off, int32_t* first_chunk, int32_t* num_chunks,
+                     int64_t* total_elems, int32_t* total_chunks, int32_t* chunk_seg);
+
+/* The one hot kernel.  Replaces, depending on op/phase/flags:
+ *   SGLD._step_fn            mcmc/sgld.py:119-154
+ *   VerletSGLD._step_fn      mcmc/verlet_sgld.py:149-197 (+ _save_state :72-83,
+ *                            _point_energy :44-47)
+ *   HMC._step_fn             mcmc/hmc.py:41-79
+ *   SGLD.sample_momentum     mcmc/sgld.py:57-69
+ *   dot()                    mcmc/sgld.py:9-11
+ *   Prior.log_prob + autograd for Normal/Laplace/StudentT
+ *                            prior/base.py:57-58, prior/loc_scale.py:34-77,
+ *                            models/base.py:72-77, inference.py:218-220        */
+int bnnp_launch(const BnnpLaunch* args, void* stream);
+
+/* VerletSGLD.maybe_reject's restore (mcmc/verlet_sgld.py:63-69):
+ * P,G,M <- prev_*  over `total` floats (prev_m/M may be null: momentum == 0). */
+int bnnp_rollback(float* P, float* G, float* M, const float* prev_p, const float* prev_g,
+                  const float* prev_m, int64_t total, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNNP_H */

@@ -207,3 +207,89 @@ class OracleEngine:
             prev_new_momentum_delta=[s.prev_new_momentum_delta for s in segs],
             square_avg_mean=[None if s.square_avg is None else float(np.mean(s.square_avg, dtype=np.float64))
                              for s in segs])
+
+
+# ---------------------------------------------------------------------------
+class CudaEngine:
+    """Adapter around the product samplers (bnn_priors_b200.mcmc) on cuda:0: the
+    same calls the trace recorded, made through the reference-shaped Python API,
+    every one of them ending in `bnnp_launch` of libbnnp.so."""
+
+    def __init__(self, trace: Trace, fused_prior: bool = False, foreign_grads: bool = False):
+        import torch
+        from bnn_priors_b200 import mcmc
+        self.torch = torch
+        dev = torch.device("cuda", 0)
+        p0 = trace.split(trace.arr(trace.meta["p0"]))
+        self.params = [torch.nn.Parameter(torch.tensor(np.asarray(a, dtype=np.float32).reshape(s), device=dev))
+                       for a, s in zip(p0, trace.shapes)]
+        c = dict(trace.ctor)
+        self.kind = trace.sampler
+        self.opt = getattr(mcmc, self.kind)(self.params, **c, seed=1234)
+        self.foreign_grads = foreign_grads
+        self.fused = fused_prior
+        if fused_prior:
+            (fg,) = self.opt.flat_groups
+            for i, spec in enumerate(trace.priors):
+                fg.set_prior(i, spec["kind"], spec["loc"], spec["scale"], spec["df"])
+            fg.prior_fused = True
+
+    def set_group(self, g):
+        for pg in self.opt.param_groups:
+            pg["lr"] = g["lr"]
+            pg["temperature"] = g["temperature"]
+
+    def set_preconditioners(self, values):
+        for p, v in zip(self.params, values):
+            self.opt.state[p]["preconditioner"] = float(v)
+
+    def preconditioners(self):
+        return [self.opt.state[p]["preconditioner"] for p in self.params]
+
+    def set_grad(self, grads):
+        torch = self.torch
+        for p, g in zip(self.params, grads):
+            t = torch.tensor(np.asarray(g, dtype=np.float32).reshape(tuple(p.shape)), device=p.device)
+            if p.grad is None or self.foreign_grads:
+                p.grad = t            # a tensor the sampler has never seen: must be adopted
+            else:
+                p.grad.copy_(t)       # in place, like autograd accumulation into the flat view
+
+    def call(self, op, kwargs, args, noise, u):
+        torch, opt = self.torch, self.opt
+        if noise is not None:
+            opt.set_replay_noise([torch.tensor(np.asarray(n, dtype=np.float32)) for n in noise])
+        if op == "maybe_reject":
+            real_rand = torch.rand
+            if u is not None:
+                torch.rand = lambda *a, **k: torch.tensor(u, dtype=torch.float32)
+            try:
+                return opt.maybe_reject(args[0])
+            finally:
+                torch.rand = real_rand
+        if op == "delta_energy":
+            return opt.delta_energy(args[0], args[1])
+        return getattr(opt, op)(**kwargs)
+
+    def _cat(self, tensors):
+        return np.concatenate([t.detach().reshape(-1).cpu().numpy() for t in tensors])
+
+    def p_flat(self):
+        return self._cat(self.params)
+
+    def m_flat(self):
+        out = []
+        for p in self.params:
+            m = self.opt.state[p].get("momentum_buffer")
+            out.append(m if m is not None else self.torch.zeros_like(p))
+        return self._cat(out)
+
+    def scalars(self):
+        from bnn_priors_b200 import _native as N
+        st = self.opt.state
+        keys = ("preconditioner", "est_temperature", "est_config_temp", "delta_energy",
+                "prev_new_momentum_delta")
+        out = {k: [st[p].get(k) for p in self.params] for k in keys}
+        (fg,) = self.opt.flat_groups
+        out["square_avg_mean"] = [float(v) for v in fg.fetch()[:, N.S_SQ_MEAN]]
+        return out
