@@ -11,10 +11,11 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libbnnp.so")
+# BNNP_LIB: load another build of the same ABI (tuning experiments with other tile sizes)
+LIB_PATH = os.environ.get("BNNP_LIB") or os.path.join(HERE, "_lib", "libbnnp.so")
 
 # ---- constants of include/bnnp.h (tests/test_abi.py checks them against the header)
-ABI_VERSION = 2
+ABI_VERSION = 3
 SEG_ALIGN = 32
 THREADS = 256
 UNROLL = 4
@@ -40,6 +41,7 @@ F_NOISE_FIRST = 1 << 9
 F_MM_PRE_NOISE = 1 << 10
 F_UPDATE_SQ = 1 << 11
 F_PRIOR_GRAD = 1 << 12
+F_ALL_SUMS = 1 << 13
 
 (S_DELTA_ENERGY, S_PREV_NEW_MOM, S_EST_MM, S_EST_PG, S_SUM_GG, S_SUM_MM, S_SQ_MEAN,
  S_LOG_PRIOR, S_GM_OLD, S_GM_NEW, S_MM_OLD, S_MM_NEW, S_NONFINITE, S_LAUNCHES) = range(14)
@@ -93,7 +95,7 @@ def lib() -> C.CDLL:
     l.bnnp_abi_version.restype = C.c_int
     l.bnnp_last_error.restype = C.c_char_p
     l.bnnp_device_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    l.bnnp_max_ctas_per_sm.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    l.bnnp_max_ctas_per_sm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     l.bnnp_plan_layout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p]
     l.bnnp_launch.argtypes = [C.POINTER(BnnpLaunch), C.c_void_p]

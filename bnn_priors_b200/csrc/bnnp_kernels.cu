@@ -39,11 +39,14 @@ int fail_cuda(cudaError_t e, const char* where) {
     return (int)e;
 }
 
-constexpr int THREADS = BNNP_THREADS;
+constexpr int THREADS = BNNP_THREADS;   // (-DBNNP_THREADS / -DBNNP_UNROLL override the header for tuning builds)
 constexpr int UNROLL = BNNP_UNROLL;
+#ifndef BNNP_MIN_CTAS
+#define BNNP_MIN_CTAS 4   // resident CTAs per SM for the hot variants (measured: tools/tune_tiles.py,
+#endif                    // profiles/r01_tile_sweep.md); 64 registers per thread at 256 threads
 constexpr int CHUNK = BNNP_CHUNK;
 constexpr int NWARPS = THREADS / 32;
-static_assert(NWARPS == BNNP_NRED, "the segment epilogue maps one warp to one partial sum");
+static_assert(THREADS % 32 == 0 && THREADS >= 32, "whole warps");
 
 // indices of the per-chunk partial sums
 enum { R_GM_OLD = 0, R_GM_NEW, R_MM_OLD, R_MM_NEW, R_PG, R_GG, R_LOGP, R_NONFINITE };
@@ -71,11 +74,12 @@ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32
                                               const PhiloxKeys& k) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k.k0[r];
-        const uint32_t n2 = hi0 ^ c3 ^ k.k1[r];
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        // 32x32 -> 64-bit products: one IMAD.WIDE each
+        const uint64_t p0 = (uint64_t)0xD2511F53u * (uint64_t)c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * (uint64_t)c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.k0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.k1[r];
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
     }
 }
 
@@ -134,21 +138,23 @@ __device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double i
 
 // -(1/N) d log p / d theta: what potential = loss - log_prior/N (models/base.py:76)
 // adds to p.grad through autograd in the reference.
+template <int KIND>
 __device__ __forceinline__ float prior_grad_term(const PriorConst& pc, float p) {
     const float d = p - pc.loc;
-    if (pc.kind == BNNP_PRIOR_NORMAL) return d * pc.k;
-    if (pc.kind == BNNP_PRIOR_LAPLACE) return d == 0.0f ? 0.0f : copysignf(pc.k, d);
-    if (pc.kind == BNNP_PRIOR_STUDENT_T) return (pc.a * d) / fmaf(d, d, pc.b) * pc.k;
+    if (KIND == BNNP_PRIOR_NORMAL) return d * pc.k;
+    if (KIND == BNNP_PRIOR_LAPLACE) return d == 0.0f ? 0.0f : copysignf(pc.k, d);
+    if (KIND == BNNP_PRIOR_STUDENT_T) return (pc.a * d) / fmaf(d, d, pc.b) * pc.k;
     return 0.0f;
 }
 
 // the theta-dependent part of log p(theta); the per-element constant is added once
 // per segment in the epilogue (log_prior_const)
+template <int KIND>
 __device__ __forceinline__ float log_prior_term(const PriorConst& pc, float p) {
     const float z = (p - pc.loc) * pc.inv_s;
-    if (pc.kind == BNNP_PRIOR_NORMAL) return -0.5f * z * z;
-    if (pc.kind == BNNP_PRIOR_LAPLACE) return -fabsf(z);
-    if (pc.kind == BNNP_PRIOR_STUDENT_T) return -0.5f * pc.a * log1pf(z * z * pc.inv_df);
+    if (KIND == BNNP_PRIOR_NORMAL) return -0.5f * z * z;
+    if (KIND == BNNP_PRIOR_LAPLACE) return -fabsf(z);
+    if (KIND == BNNP_PRIOR_STUDENT_T) return -0.5f * pc.a * log1pf(z * z * pc.inv_df);
     return 0.0f;
 }
 
@@ -189,56 +195,109 @@ struct Coef {
     float cm, cgM, cn, cpM, gmax;
 };
 
-// One float4 of every stream.  MASKED is the (rare) quad that straddles the end of
-// its segment: lanes >= `valid` are padding and must come out as zeros.
-template <int NOISE, bool PRIOR, bool MASKED>
+// which dot products a launch needs (compile time: every one costs an FMA per element
+// and ten shuffle steps per warp)
+enum { SUMS_MIN = 0,      // g.g and the non-finite probe
+       SUMS_VERLET = 1,   // + g.m, g.m'   (verlet_sgld.py:174-176)
+       SUMS_ALL = 2 };    // + m.m, m'.m', p.g, sum log p
+
+// One float4 of every stream.  Lanes >= `valid` (only the quad that straddles the end
+// of a segment has valid < 4) arrive zeroed and stay zero.
+template <int NOISE, bool PRIOR, int KIND, bool NOISE_FIRST, int SUMS>
 __device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c, const PriorConst& pc, int valid,
                                             F4& p, const F4& g, F4& m, const float eps[4], float acc[BNNP_NRED]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const bool ok = !MASKED || j < valid;
-        const float p0 = ok ? p.f[j] : 0.0f;
-        const float m0 = ok ? m.f[j] : 0.0f;
-        float gj = ok ? g.f[j] : 0.0f;
-        const float e = (NOISE != BNNP_NOISE_NONE && ok) ? eps[j] : 0.0f;
+        const float p0 = p.f[j], m0 = m.f[j];
+        float gj = g.f[j];
         acc[R_NONFINITE] = fmaf(gj, 0.0f, acc[R_NONFINITE]);   // 0, or NaN once g is inf/NaN
         if (PRIOR) {
-            if ((flags & BNNP_F_PRIOR_GRAD) && ok) gj += prior_grad_term(pc, p0);
+            if (KIND != BNNP_PRIOR_NONE && (flags & BNNP_F_PRIOR_GRAD) && j < valid) gj += prior_grad_term<KIND>(pc, p0);
             if (flags & BNNP_F_CLAMP_GRAD) gj = fminf(fmaxf(gj, -c.gmax), c.gmax);
         }
         float t, pre;
-        if (flags & BNNP_F_NOISE_FIRST) {
-            t = c.cn * e;
+        if (NOISE_FIRST) {           // verlet_sgld.py:163-167
+            t = (NOISE != BNNP_NOISE_NONE) ? c.cn * eps[j] : 0.0f;
             t = fmaf(c.cgM, gj, t);
             if (c.cm != 0.0f) t = fmaf(c.cm, m0, t);
             pre = t;
-        } else {
+        } else {                     // sgld.py:129,142 ; hmc.py:66 ; sgld.py:69
             t = c.cm * m0;
             t = fmaf(c.cgM, gj, t);
             pre = t;
-            if (NOISE != BNNP_NOISE_NONE) t = fmaf(c.cn, e, t);
+            if (NOISE != BNNP_NOISE_NONE) t = fmaf(c.cn, eps[j], t);
         }
-        acc[R_GM_OLD] = fmaf(gj, m0, acc[R_GM_OLD]);
-        acc[R_GM_NEW] = fmaf(gj, t, acc[R_GM_NEW]);
-        const float mo = (flags & BNNP_F_MM_PRE_NOISE) ? pre : m0;
-        acc[R_MM_OLD] = fmaf(mo, mo, acc[R_MM_OLD]);
-        acc[R_MM_NEW] = fmaf(t, t, acc[R_MM_NEW]);
-        acc[R_PG] = fmaf(p0, gj, acc[R_PG]);
         acc[R_GG] = fmaf(gj, gj, acc[R_GG]);
-        const float pn = (flags & BNNP_F_WRITE_P) ? fmaf(c.cpM, t, p0) : p0;
-        if (PRIOR) {
-            if ((flags & BNNP_F_LOG_PRIOR) && ok) acc[R_LOGP] += log_prior_term(pc, pn);
+        if (SUMS >= SUMS_VERLET) {
+            acc[R_GM_OLD] = fmaf(gj, m0, acc[R_GM_OLD]);
+            acc[R_GM_NEW] = fmaf(gj, t, acc[R_GM_NEW]);
+        }
+        if (SUMS >= SUMS_ALL) {
+            const float mo = (flags & BNNP_F_MM_PRE_NOISE) ? pre : m0;
+            acc[R_MM_OLD] = fmaf(mo, mo, acc[R_MM_OLD]);
+            acc[R_MM_NEW] = fmaf(t, t, acc[R_MM_NEW]);
+            acc[R_PG] = fmaf(p0, gj, acc[R_PG]);
+        }
+        const float pn = fmaf(c.cpM, t, p0);      // stored only with BNNP_F_WRITE_P
+        if (PRIOR && KIND != BNNP_PRIOR_NONE) {
+            if ((flags & BNNP_F_LOG_PRIOR) && j < valid)
+                acc[R_LOGP] += log_prior_term<KIND>(pc, (flags & BNNP_F_WRITE_P) ? pn : p0);
         }
         p.f[j] = pn;
         m.f[j] = t;
     }
 }
 
+struct ChunkCtx {
+    int64_t fbase;   // flat index of the chunk's first float
+    int rem;         // valid floats in this chunk
+    int tid;
+};
+
+// Noise + update + stores for the UNROLL quads of one thread; the prior kind is a
+// template parameter so the per-segment switch happens once per CTA.
+template <int NOISE, bool PRIOR, int KIND, bool NOISE_FIRST, int SUMS>
+__device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCtx& cx, const Coef& c,
+                                              const PriorConst& pc, const PhiloxKeys& keys, F4 (&p)[UNROLL],
+                                              F4 (&g)[UNROLL], F4 (&m)[UNROLL], F4 (&z)[UNROLL],
+                                              float acc[BNNP_NRED]) {
+    const uint32_t flags = L.flags;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int e = (u * THREADS + cx.tid) * 4;
+        if (e >= cx.rem) continue;
+        const int64_t fi = cx.fbase + e;
+        if (flags & BNNP_F_SAVE_STATE) {   // verlet_sgld.py:72-83, the values BEFORE the update
+            st_f4(L.prev_p + fi, p[u].v);
+            st_f4(L.prev_g + fi, g[u].v);
+            if (L.prev_m != nullptr) st_f4(L.prev_m + fi, m[u].v);
+        }
+        if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)fi >> 2, L.call, keys, z[u].f);
+        const int valid = cx.rem - e;
+        if (valid < 4) {   // the quad that straddles the segment end: padding lanes are zeros
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (j >= valid) p[u].f[j] = g[u].f[j] = m[u].f[j] = z[u].f[j] = 0.0f;
+        }
+        update_quad<NOISE, PRIOR, KIND, NOISE_FIRST, SUMS>(flags, c, pc, valid, p[u], g[u], m[u], z[u].f, acc);
+        if (flags & BNNP_F_WRITE_P) st_f4(L.P + fi, p[u].v);
+        if (flags & BNNP_F_WRITE_M) st_f4(L.M + fi, m[u].v);
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // The step kernel: one CTA per chunk of BNNP_CHUNK floats of one segment.
 // ---------------------------------------------------------------------------------
-template <int NOISE, bool PRIOR>
-__global__ void __launch_bounds__(THREADS) bnnp_step_kernel(const BnnpLaunch L) {
+// The production variants (no replay buffer, at most the Verlet sums) are held to
+// BNNP_MIN_CTAS resident CTAs per SM; the metrics / replay variants need more
+// registers and would only spill under that cap.
+template <int NOISE, int SUMS>
+constexpr int min_ctas() {
+    return (NOISE != BNNP_NOISE_REPLAY && SUMS != 2) ? BNNP_MIN_CTAS : (BNNP_MIN_CTAS > 3 ? 3 : BNNP_MIN_CTAS);
+}
+
+template <int NOISE, bool PRIOR, bool NOISE_FIRST, int SUMS>
+__global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS>()) bnnp_step_kernel(const BnnpLaunch L) {
     __shared__ double s_red[NWARPS][BNNP_NRED];
     __shared__ int s_last;
 
@@ -248,8 +307,10 @@ __global__ void __launch_bounds__(THREADS) bnnp_step_kernel(const BnnpLaunch L) 
     const BnnpSegment sd = L.segs[seg];
     const int64_t cbase = (int64_t)(chunk - sd.first_chunk) * CHUNK;
     const int64_t left = sd.numel - cbase;
-    const int rem = left < (int64_t)CHUNK ? (int)left : CHUNK;   // valid floats in this chunk
-    const int64_t fbase = sd.off + cbase;                          // flat index of the chunk
+    ChunkCtx cx;
+    cx.rem = left < (int64_t)CHUNK ? (int)left : CHUNK;
+    cx.fbase = sd.off + cbase;
+    cx.tid = tid;
     const uint32_t flags = L.flags;
 
     Coef c;
@@ -265,43 +326,49 @@ __global__ void __launch_bounds__(THREADS) bnnp_step_kernel(const BnnpLaunch L) 
     PhiloxKeys keys;
     if (NOISE == BNNP_NOISE_PHILOX) keys = philox_round_keys(L.key0, L.key1);
 
-    // ---- front-batched 128-bit loads: up to 3 (4 with replay noise) x UNROLL in flight per thread
+    // ---- front-batched 128-bit loads: 3 (4 with replay noise) x UNROLL in flight per thread
     F4 p[UNROLL], g[UNROLL], m[UNROLL], z[UNROLL];
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const int e = (u * THREADS + tid) * 4;
-        const bool act = e < rem;
-        p[u].v = (act && (flags & BNNP_F_READ_P)) ? ld_f4(L.P + fbase + e) : zero4;
-        g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_f4(L.G + fbase + e) : zero4;
-        m[u].v = (act && (flags & BNNP_F_READ_M)) ? ld_f4(L.M + fbase + e) : zero4;
-        if (NOISE == BNNP_NOISE_REPLAY) z[u].v = act ? ld_f4(L.replay_noise + fbase + e) : zero4;
+        const bool act = e < cx.rem;
+        p[u].v = (act && (flags & BNNP_F_READ_P)) ? ld_f4(L.P + cx.fbase + e) : zero4;
+        g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_f4(L.G + cx.fbase + e) : zero4;
+        m[u].v = (act && (flags & BNNP_F_READ_M)) ? ld_f4(L.M + cx.fbase + e) : zero4;
+        if (NOISE == BNNP_NOISE_REPLAY) z[u].v = act ? ld_f4(L.replay_noise + cx.fbase + e) : zero4;
+        else z[u].v = zero4;
     }
 
     float acc[BNNP_NRED];
 #pragma unroll
     for (int k = 0; k < BNNP_NRED; ++k) acc[k] = 0.0f;
 
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-        const int e = (u * THREADS + tid) * 4;
-        if (e >= rem) continue;
-        if (flags & BNNP_F_SAVE_STATE) {   // verlet_sgld.py:72-83, the values BEFORE the update
-            st_f4(L.prev_p + fbase + e, p[u].v);
-            st_f4(L.prev_g + fbase + e, g[u].v);
-            if (L.prev_m != nullptr) st_f4(L.prev_m + fbase + e, m[u].v);
+    if (PRIOR) {
+        switch (pc.kind) {
+            case BNNP_PRIOR_NORMAL:
+                process_chunk<NOISE, true, BNNP_PRIOR_NORMAL, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+                break;
+            case BNNP_PRIOR_LAPLACE:
+                process_chunk<NOISE, true, BNNP_PRIOR_LAPLACE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+                break;
+            case BNNP_PRIOR_STUDENT_T:
+                process_chunk<NOISE, true, BNNP_PRIOR_STUDENT_T, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+                break;
+            default:
+                process_chunk<NOISE, true, BNNP_PRIOR_NONE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
         }
-        if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)(fbase + e) >> 2, L.call, keys, z[u].f);
-        const int valid = rem - e;
-        if (valid >= 4) update_quad<NOISE, PRIOR, false>(flags, c, pc, 4, p[u], g[u], m[u], z[u].f, acc);
-        else update_quad<NOISE, PRIOR, true>(flags, c, pc, valid, p[u], g[u], m[u], z[u].f, acc);
-        if (flags & BNNP_F_WRITE_P) st_f4(L.P + fbase + e, p[u].v);
-        if (flags & BNNP_F_WRITE_M) st_f4(L.M + fbase + e, m[u].v);
+    } else {
+        process_chunk<NOISE, false, BNNP_PRIOR_NONE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
     }
 
     // ---- chunk reduction: fp32 butterfly inside the warp, fp64 across warps (fixed order)
+    constexpr unsigned LIVE = (SUMS == SUMS_ALL) ? 0xffu
+                              : (SUMS == SUMS_VERLET) ? ((1u << R_GG) | (1u << R_NONFINITE) | (1u << R_GM_OLD) | (1u << R_GM_NEW))
+                                                      : ((1u << R_GG) | (1u << R_NONFINITE));
 #pragma unroll
     for (int k = 0; k < BNNP_NRED; ++k) {
+        if (!((LIVE | (PRIOR ? (1u << R_LOGP) : 0u)) >> k & 1u)) continue;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
     }
@@ -328,12 +395,12 @@ __global__ void __launch_bounds__(THREADS) bnnp_step_kernel(const BnnpLaunch L) 
 
     // ---- segment epilogue, run by the last CTA of this segment to finish
     __threadfence();
-    {
-        const double* base = L.partials + (int64_t)sd.first_chunk * BNNP_NRED + warp;   // warp w sums value w
+    for (int k = warp; k < BNNP_NRED; k += NWARPS) {   // one warp per partial sum, fixed order
+        const double* base = L.partials + (int64_t)sd.first_chunk * BNNP_NRED + k;
         double s = 0.0;
         for (int ch = lane; ch < sd.num_chunks; ch += 32) s += ld_cg_f64(base + (int64_t)ch * BNNP_NRED);
         s = warp_sum_f64(s);
-        if (lane == 0) s_red[0][warp] = s;
+        if (lane == 0) s_red[0][k] = s;
     }
     __syncthreads();
     if (tid != 0) return;
@@ -343,17 +410,21 @@ __global__ void __launch_bounds__(THREADS) bnnp_step_kernel(const BnnpLaunch L) 
     const double pg = s_red[0][R_PG], gg = s_red[0][R_GG];
     double* st = L.seg_state + (int64_t)seg * BNNP_STATE_STRIDE;
     const double M = sd.precond;
-    const bool metrics = flags & BNNP_F_CALC_METRICS;
+    const bool metrics = (flags & BNNP_F_CALC_METRICS) && SUMS == SUMS_ALL;
 
-    st[BNNP_S_GM_OLD] = gm_old;
-    st[BNNP_S_GM_NEW] = gm_new;
-    st[BNNP_S_MM_OLD] = mm_old;
-    st[BNNP_S_MM_NEW] = mm_new;
+    if (SUMS >= SUMS_VERLET) {
+        st[BNNP_S_GM_OLD] = gm_old;
+        st[BNNP_S_GM_NEW] = gm_new;
+    }
+    if (SUMS == SUMS_ALL) {
+        st[BNNP_S_MM_OLD] = mm_old;
+        st[BNNP_S_MM_NEW] = mm_new;
+    }
     if (flags & BNNP_F_READ_G) {
         st[BNNP_S_SUM_GG] = gg;
         st[BNNP_S_NONFINITE] = (s_red[0][R_NONFINITE] == 0.0) ? 0.0 : 1.0;
     }
-    if (L.op == BNNP_OP_VERLET) {
+    if (L.op == BNNP_OP_VERLET && SUMS >= SUMS_VERLET) {
         const double c_gm = L.c_gm_base * M;                       // verlet_sgld.py:170
         if (L.phase == BNNP_PHASE_INITIAL) {
             st[BNNP_S_DELTA_ENERGY] = -((M * M) * L.curv_base * gg);   // :171-172 with :44-47
@@ -366,14 +437,16 @@ __global__ void __launch_bounds__(THREADS) bnnp_step_kernel(const BnnpLaunch L) 
         st[BNNP_S_PREV_NEW_MOM] = c_gm * gm_new;                    // :176
         if (metrics) st[BNNP_S_EST_MM] = (L.phase == BNNP_PHASE_FINAL) ? mm_new : mm_old;   // :181-187
     } else if (L.op == BNNP_OP_HMC) {
-        if (L.phase == BNNP_PHASE_INITIAL) st[BNNP_S_DELTA_ENERGY] = -0.5 * mm_old;         // hmc.py:50-53
+        if (L.phase == BNNP_PHASE_INITIAL && SUMS == SUMS_ALL) st[BNNP_S_DELTA_ENERGY] = -0.5 * mm_old;   // hmc.py:50-53
         if (metrics) st[BNNP_S_EST_MM] = (L.phase == BNNP_PHASE_FINAL) ? mm_new : mm_old;   // :55,60,72
     } else if (L.op == BNNP_OP_SGLD) {
         if (metrics) st[BNNP_S_EST_MM] = mm_old;                    // sgld.py:127,137
     }
     if (metrics && L.op <= BNNP_OP_HMC) st[BNNP_S_EST_PG] = pg;     // sgld.py:146
-    if (flags & BNNP_F_WRITE_M) st[BNNP_S_SUM_MM] = mm_new;
-    else if (flags & BNNP_F_READ_M) st[BNNP_S_SUM_MM] = mm_old;
+    if (SUMS == SUMS_ALL) {
+        if (flags & BNNP_F_WRITE_M) st[BNNP_S_SUM_MM] = mm_new;
+        else if (flags & BNNP_F_READ_M) st[BNNP_S_SUM_MM] = mm_old;
+    }
     if (flags & BNNP_F_UPDATE_SQ)                                   // sgld.py:153-154, through its mean
         st[BNNP_S_SQ_MEAN] = L.rms_alpha * st[BNNP_S_SQ_MEAN] + (1.0 - L.rms_alpha) * (gg / (double)sd.numel);
     if (PRIOR && (flags & BNNP_F_LOG_PRIOR))
@@ -401,13 +474,36 @@ __global__ void __launch_bounds__(THREADS) bnnp_rollback_kernel(float* __restric
 
 typedef void (*StepKernel)(const BnnpLaunch);
 
-StepKernel pick_kernel(int noise, bool prior) {
-    switch (noise) {
-        case BNNP_NOISE_NONE: return prior ? bnnp_step_kernel<BNNP_NOISE_NONE, true> : bnnp_step_kernel<BNNP_NOISE_NONE, false>;
-        case BNNP_NOISE_REPLAY: return prior ? bnnp_step_kernel<BNNP_NOISE_REPLAY, true> : bnnp_step_kernel<BNNP_NOISE_REPLAY, false>;
-        case BNNP_NOISE_PHILOX: return prior ? bnnp_step_kernel<BNNP_NOISE_PHILOX, true> : bnnp_step_kernel<BNNP_NOISE_PHILOX, false>;
+template <int NOISE, bool PRIOR, bool NF>
+StepKernel pick_sums(int sums) {
+    switch (sums) {
+        case SUMS_MIN: return bnnp_step_kernel<NOISE, PRIOR, NF, SUMS_MIN>;
+        case SUMS_VERLET: return bnnp_step_kernel<NOISE, PRIOR, NF, SUMS_VERLET>;
+        case SUMS_ALL: return bnnp_step_kernel<NOISE, PRIOR, NF, SUMS_ALL>;
     }
     return nullptr;
+}
+
+template <int NOISE>
+StepKernel pick_noise(bool prior, bool noise_first, int sums) {
+    if (prior) return noise_first ? pick_sums<NOISE, true, true>(sums) : pick_sums<NOISE, true, false>(sums);
+    return noise_first ? pick_sums<NOISE, false, true>(sums) : pick_sums<NOISE, false, false>(sums);
+}
+
+StepKernel pick_kernel(int noise, bool prior, bool noise_first, int sums) {
+    switch (noise) {
+        case BNNP_NOISE_NONE: return pick_noise<BNNP_NOISE_NONE>(prior, noise_first, sums);
+        case BNNP_NOISE_REPLAY: return pick_noise<BNNP_NOISE_REPLAY>(prior, noise_first, sums);
+        case BNNP_NOISE_PHILOX: return pick_noise<BNNP_NOISE_PHILOX>(prior, noise_first, sums);
+    }
+    return nullptr;
+}
+
+// which dot products the epilogue of (op, flags) reads
+int sums_needed(int op, uint32_t flags) {
+    if (flags & (BNNP_F_CALC_METRICS | BNNP_F_ALL_SUMS)) return SUMS_ALL;
+    if (op == BNNP_OP_SAMPLE_MOMENTUM || op == BNNP_OP_REDUCE) return SUMS_ALL;
+    return op == BNNP_OP_VERLET ? SUMS_VERLET : SUMS_MIN;
 }
 
 bool misaligned(const void* p) { return ((uintptr_t)p & 15u) != 0; }
@@ -429,9 +525,9 @@ int bnnp_device_info(int device, int* sm_count, int* l2_bytes) {
     return 0;
 }
 
-int bnnp_max_ctas_per_sm(int noise, int has_prior, int* out) {
-    StepKernel k = pick_kernel(noise, has_prior != 0);
-    if (k == nullptr || out == nullptr) return fail(BNNP_E_ARG, "bnnp_max_ctas_per_sm: bad noise kind");
+int bnnp_max_ctas_per_sm(int noise, int has_prior, int noise_first, int sums, int* out) {
+    StepKernel k = pick_kernel(noise, has_prior != 0, noise_first != 0, sums);
+    if (k == nullptr || out == nullptr) return fail(BNNP_E_ARG, "bnnp_max_ctas_per_sm: bad variant");
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, THREADS, 0);
     if (e != cudaSuccess) return fail_cuda(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     return 0;
@@ -481,7 +577,7 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
         return fail(BNNP_E_ALIGN, "bnnp_launch: flat arrays must be 16-byte aligned");
     const bool prior = (f & (BNNP_F_LOG_PRIOR | BNNP_F_PRIOR_GRAD)) != 0;
     if (prior && !(f & BNNP_F_READ_P)) return fail(BNNP_E_ARG, "bnnp_launch: the prior needs READ_P");
-    StepKernel k = pick_kernel(a->noise, prior);
+    StepKernel k = pick_kernel(a->noise, prior, (f & BNNP_F_NOISE_FIRST) != 0, sums_needed(a->op, f));
     if (k == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: bad noise kind");
     k<<<a->nchunks, THREADS, 0, (cudaStream_t)stream>>>(*a);
     cudaError_t e = cudaGetLastError();

@@ -399,15 +399,19 @@ class FlatGroup:
     def _p_version(self) -> int:
         return sum(p._version for p in self.params)
 
-    def note_step_sums(self, lp_computed: bool) -> None:
-        """Called after a step launch: SUM_GG / SUM_MM in the segment state now
-        describe G (the gradient the step used) and M as stored; LOG_PRIOR describes
-        P as stored if the launch carried BNNP_F_LOG_PRIOR."""
+    def note_step_sums(self, flags: int, op: int) -> None:
+        """Called after a step launch: SUM_GG in the segment state now describes G
+        (the gradient the step used); SUM_MM describes M as stored if the launch
+        reduced every sum; LOG_PRIOR describes P as stored if it carried
+        BNNP_F_LOG_PRIOR."""
         self._gg_version = self.G._version
-        self._mm_version = self.M._version if self.M is not None else None
-        if lp_computed:
+        all_sums = bool(flags & (N.F_CALC_METRICS | N.F_ALL_SUMS)) or op in (N.OP_SAMPLE_MOMENTUM, N.OP_REDUCE)
+        self._mm_version = self.M._version if (self.M is not None and all_sums) else None
+        if flags & N.F_LOG_PRIOR:
             self._lp_valid = True
             self._lp_pversion = self._p_version()
+        elif flags & N.F_WRITE_P:
+            self._lp_valid = False
 
     def invalidate_sums(self) -> None:
         self._gg_version = self._mm_version = None

@@ -59,6 +59,8 @@ class HMC(VerletSGLD):
         flags = N.F_READ_P | N.F_READ_G | N.F_READ_M | N.F_WRITE_M | pf
         if calc_metrics:
             flags |= N.F_CALC_METRICS
+        if is_initial or is_final:
+            flags |= N.F_ALL_SUMS        # the kinetic energy .5 m.m enters delta_energy (:50-53, :32-33)
         if save_state:
             fg.ensure_prev_storage(with_momentum=True)
             flags |= N.F_SAVE_STATE
@@ -74,4 +76,4 @@ class HMC(VerletSGLD):
             fg.metrics_num_data = group['num_data']
         if is_initial:
             fg.have_delta = True
-        fg.note_step_sums(bool(pf) and not is_final)
+        fg.note_step_sums(flags, self._OP)

@@ -226,7 +226,7 @@ class SGLD(torch.optim.Optimizer):
         if calc_metrics:
             fg.have_metrics = True
             fg.metrics_num_data = group['num_data']
-        fg.note_step_sums(bool(pf) and not is_final)
+        fg.note_step_sums(flags, self._OP)
 
     # ------------------------------------------------------------------ preconditioner
     @torch.no_grad()

@@ -193,4 +193,4 @@ class VerletSGLD(SGLD):
         fg.have_prev_new = True
         if is_initial:
             fg.have_delta = True
-        fg.note_step_sums(bool(pf) and not is_final)
+        fg.note_step_sums(flags, self._OP)

@@ -30,11 +30,15 @@
 extern "C" {
 #endif
 
-#define BNNP_ABI_VERSION 2
+#define BNNP_ABI_VERSION 3
 
 #define BNNP_SEG_ALIGN 32      /* floats: every segment starts on a 128-byte line */
+#ifndef BNNP_THREADS
 #define BNNP_THREADS 256       /* threads per CTA                                 */
+#endif
+#ifndef BNNP_UNROLL
 #define BNNP_UNROLL 4          /* 128-bit accesses per thread per stream          */
+#endif
 #define BNNP_CHUNK (BNNP_THREADS * BNNP_UNROLL * 4)   /* 4096 floats per CTA      */
 
 #define BNNP_NRED 8            /* partial sums per chunk                          */
@@ -76,8 +80,12 @@ enum {
     BNNP_F_MM_PRE_NOISE = 1u << 10, /* sgld.py:132-137 (momentum == 0): the metric is
                                        dot(m', m') before the noise is added         */
     BNNP_F_UPDATE_SQ = 1u << 11,    /* square_avg moving average, sgld.py:153-154    */
-    BNNP_F_PRIOR_GRAD = 1u << 12    /* g <- g - (1/N) dlog p/dtheta in-register: models/
+    BNNP_F_PRIOR_GRAD = 1u << 12,   /* g <- g - (1/N) dlog p/dtheta in-register: models/
                                        base.py:72-77 + inference.py:218 without autograd */
+    BNNP_F_ALL_SUMS = 1u << 13      /* reduce every dot product even without CALC_METRICS
+                                       (HMC initial/final need m.m: hmc.py:50-53,32-33);
+                                       otherwise a launch only reduces what its epilogue
+                                       reads: g.g always, g.m and g.m' for VERLET       */
 };
 
 /* noise source */
@@ -145,8 +153,9 @@ const char* bnnp_last_error(void);
 
 /* SM count and L2 size of a device (grid sizing, bench bookkeeping). */
 int bnnp_device_info(int device, int* sm_count, int* l2_bytes);
-/* Resident CTAs per SM of the step-kernel instantiation (noise, has_prior). */
-int bnnp_max_ctas_per_sm(int noise, int has_prior, int* out);
+/* Resident CTAs per SM of one step-kernel instantiation: noise kind, prior fused or
+ * not, BNNP_F_NOISE_FIRST or not, sums = 0 (g.g only) / 1 (+ g.m, g.m') / 2 (all). */
+int bnnp_max_ctas_per_sm(int noise, int has_prior, int noise_first, int sums, int* out);
 
 /* Host helper (no GPU needed): flat-layout offsets and chunk table for `nseg`
  * tensors.  Fills off[nseg], first_chunk[nseg], num_chunks[nseg]; returns the

@@ -1,0 +1,132 @@
+"""The C-ABI boundary on a machine without a GPU: the library loads, exports every
+symbol include/bnnp.h declares, the Python mirror of the header's constants is in
+step with it, the host-side planner works and argument validation fails cleanly
+(negative code + message) before anything touches CUDA."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bnn_priors_b200 import _native as N
+from bnn_priors_b200 import build as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "include", "bnnp.h")).read()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    B.build()
+    return N.lib()
+
+
+def _declared_functions():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(bnnp_[a-z_0-9]+)\s*\(", body)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = _declared_functions()
+    assert set(names) == set(N.EXPORTS)
+    for n in names:
+        assert getattr(lib, n) is not None
+    assert lib.bnnp_abi_version() == N.ABI_VERSION
+
+
+def test_python_constants_match_header():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    defines = dict(re.findall(r"#define\s+BNNP_([A-Z_]+)\s+(\d+)\s*$", body, flags=re.M))
+    assert int(defines["ABI_VERSION"]) == N.ABI_VERSION
+    assert int(defines["SEG_ALIGN"]) == N.SEG_ALIGN
+    assert int(defines["THREADS"]) == N.THREADS and int(defines["UNROLL"]) == N.UNROLL
+    assert int(defines["NRED"]) == N.NRED and int(defines["STATE_STRIDE"]) == N.STATE_STRIDE
+    assert N.CHUNK == N.THREADS * N.UNROLL * 4
+    # enums: explicit values and implicit counting
+    for block in re.findall(r"enum\s*\{(.*?)\}", body, flags=re.S):
+        nxt = 0
+        for item in [x.strip() for x in block.split(",") if x.strip()]:
+            m = re.match(r"BNNP_([A-Z_0-9]+)\s*(?:=\s*(.+))?$", item)
+            assert m, item
+            name, val = m.group(1), m.group(2)
+            if val is not None:
+                val = val.strip()
+                sh = re.match(r"1u\s*<<\s*(\d+)", val)
+                nxt = (1 << int(sh.group(1))) if sh else int(val)
+            if name.startswith("E_"):
+                nxt += 1
+                continue
+            assert getattr(N, name) == nxt, (name, getattr(N, name), nxt)
+            nxt += 1
+
+
+def test_struct_layouts_match_header():
+    # BnnpSegment: 3 x 8 + 3 x 4 + 3 x 4 = 48 bytes, natural alignment
+    assert N.SEGMENT_DTYPE.itemsize == 48
+    assert [N.SEGMENT_DTYPE.fields[k][1] for k in ("off", "numel", "precond", "prior_loc", "prior_kind",
+                                                   "first_chunk", "num_chunks")] == [0, 8, 16, 24, 36, 40, 44]
+    fields = re.search(r"typedef struct BnnpLaunch \{(.*?)\} BnnpLaunch;", HEADER, flags=re.S).group(1)
+    fields = re.sub(r"/\*.*?\*/", "", fields, flags=re.S)
+    names = []
+    for decl in fields.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?[A-Za-z_0-9]+\s*\**", "", decl, count=1)
+        names += [x.strip().lstrip("*").strip() for x in decl.split(",")]
+    assert names == [f[0] for f in N.BnnpLaunch._fields_]
+    assert C.sizeof(N.BnnpLaunch) % 8 == 0
+
+
+def test_plan_layout(lib):
+    numel = [10, 4096, 4097, 1, 39200, 31]
+    off, first, nch, total, chunk_seg = N.plan_layout(numel)
+    assert list(nch) == [1, 1, 2, 1, 10, 1]
+    assert list(first) == [0, 1, 2, 4, 5, 15]
+    assert all(o % N.SEG_ALIGN == 0 for o in off)
+    for i in range(len(numel) - 1):
+        assert off[i + 1] - off[i] >= numel[i] and off[i + 1] - off[i] < numel[i] + N.SEG_ALIGN
+    assert total % N.SEG_ALIGN == 0 and total >= off[-1] + numel[-1]
+    assert list(chunk_seg) == [0, 1, 2, 2, 3] + [4] * 10 + [5]
+    # empty segments are rejected with a message, not a crash
+    bad = np.array([4, 0], dtype=np.int64)
+    o, f, n = np.zeros(2, np.int64), np.zeros(2, np.int32), np.zeros(2, np.int32)
+    rc = lib.bnnp_plan_layout(bad.ctypes.data, 2, o.ctypes.data, f.ctypes.data, n.ctypes.data, None, None, None)
+    assert rc == -1 and b"empty" in lib.bnnp_last_error()
+
+
+def test_launch_validates_arguments_without_a_gpu(lib):
+    assert lib.bnnp_launch(None, None) == -1
+    a = N.BnnpLaunch()
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"empty chain" in lib.bnnp_last_error()
+    a.nseg, a.nchunks = 1, 1
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"null table" in lib.bnnp_last_error()
+    for f in ("segs", "chunk_seg", "seg_state", "partials", "tickets"):
+        setattr(a, f, 4096)
+    a.op = 9
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"bad op" in lib.bnnp_last_error()
+    a.op, a.flags = N.OP_SGLD, N.F_READ_P
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"P is null" in lib.bnnp_last_error()
+    a.P, a.flags = 4096 + 4, N.F_READ_P
+    assert lib.bnnp_launch(C.byref(a), None) == -2 and b"16-byte" in lib.bnnp_last_error()
+    a.P, a.flags = 4096, N.F_READ_P | N.F_SAVE_STATE
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"SAVE_STATE" in lib.bnnp_last_error()
+    a.flags, a.noise = N.F_READ_P, N.NOISE_REPLAY
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"replay" in lib.bnnp_last_error()
+    assert lib.bnnp_rollback(None, None, None, None, None, None, 0, None) == -1
+
+
+def test_philox_key_matches_the_oracle_specification():
+    from oracle import sgmcmc_oracle as O
+    for seed, stream in [(0, 0), (1234, 7), (2**63 + 5, 65536 * 3 + 1)]:
+        assert N.philox_key(seed, stream) == O.philox_key(seed, stream)
+
+
+def test_samplers_refuse_cpu_tensors():
+    import torch
+    from bnn_priors_b200 import mcmc
+    for cls, kw in ((mcmc.SGLD, dict(lr=.1, num_data=1)), (mcmc.VerletSGLD, dict(lr=.1, num_data=1)),
+                    (mcmc.HMC, dict(lr=.1, num_data=1))):
+        with pytest.raises(RuntimeError, match="CUDA tensors only"):
+            cls([torch.nn.Parameter(torch.zeros(3))], **kw)

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Kernel time of the main transitions for one build of libbnnp.so (BNNP_LIB picks
+it): used to choose BNNP_THREADS / BNNP_UNROLL / BNNP_MIN_CTAS.  GPU box only.
+
+    for f in bnn_priors_b200/_lib/tune/*.so; do BNNP_LIB=$PWD/$f python tools/tune_tiles.py; done
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+dev = torch.device("cuda", 0)
+K = int(os.environ.get("TUNE_STEPS", "100"))
+out = {"lib": os.path.basename(os.environ.get("BNNP_LIB", "default"))}
+cases = (("sgld", "SGLD", False, lambda o: o.step(calc_metrics=False)),
+         ("sgld_metrics", "SGLD", False, lambda o: o.step(calc_metrics=True)),
+         ("verlet", "VerletSGLD", False, lambda o: o.step(calc_metrics=False)),
+         ("verlet_fused", "VerletSGLD", True, lambda o: o.step(calc_metrics=False)),
+         ("verlet_save", "VerletSGLD", False, lambda o: o.initial_step(save_state=True, calc_metrics=False)),
+         ("hmc", "HMC", False, lambda o: o.step(calc_metrics=False)))
+only = os.environ.get("TUNE_CASES")
+for name, smp, fused, call in cases:
+    if only and name not in only.split(","):
+        continue
+    opt, params, fg = bench.make_chain(dev, 0, smp, fused_prior=fused)
+    call(opt)
+    for _ in range(200):
+        fg.relaunch()
+    ms = sorted(bench.timed_gpu(fg.relaunch, K, dev, False) / K for _ in range(5))
+    out[name] = [round(ms[0] * 1e3, 2), round(ms[2] * 1e3, 2)]      # min, median of 5
+    del opt, params, fg
+    torch.cuda.empty_cache()
+print(json.dumps(out), flush=True)
