@@ -42,8 +42,8 @@ class VerletSGLD(SGLD):
         """Make SUM_GG (and SUM_MM) in the segment state describe the current
         p.grad / momentum: free right after a step, one read-only launch if
         somebody changed them since."""
+        fg.sync_views(raise_on_no_grad=True)     # a re-bound p.grad is copied in (and bumps the version)
         if not fg.sums_fresh(need_mm=self._OP == N.OP_HMC):
-            fg.sync_views(raise_on_no_grad=True)
             fg.reduce_now(1.0 / group['num_data'] if fg.prior_fused else 0.0)
 
     def delta_energy(self, prev_potential: float, potential: float) -> float:

@@ -1,0 +1,134 @@
+"""Tiny stand-ins for the reference's model / prior classes, for the GPU tests
+(the GPU box has no reference checkout).  They follow the reference's
+INTERFACES -- `Prior` modules holding the parameter as `.p` with constant
+`loc` / `scale` / `df` buffers and a `_dist` (prior/base.py:17-76), models with
+`log_prior()`, `log_likelihood()` and `split_potential_and_acc()`
+(models/base.py:25-77,187-191) -- written from scratch.  Test infrastructure only.
+"""
+import math
+
+import torch
+import torch.distributions as td
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class Prior(nn.Module):
+    _dist = None
+
+    def __init__(self, shape, **kwargs):
+        super().__init__()
+        self.kwargs_keys = list(kwargs)
+        for k, v in kwargs.items():
+            if isinstance(v, nn.Parameter):
+                self.register_parameter(k, v)
+            else:
+                self.register_buffer(k, torch.as_tensor(v, dtype=torch.float32))
+        self.p = nn.Parameter(self._dist_obj().sample(torch.Size(shape)))
+
+    def _dist_obj(self):
+        return self._dist(**{k: getattr(self, k) for k in self.kwargs_keys})
+
+    def log_prob(self):
+        return self._dist_obj().log_prob(self.p).sum()
+
+    def forward(self):
+        return self.p
+
+
+class Normal(Prior):
+    _dist = td.Normal
+
+    def __init__(self, shape, loc=0., scale=1.):
+        super().__init__(shape, loc=loc, scale=scale)
+
+
+class Laplace(Prior):
+    _dist = td.Laplace
+
+    def __init__(self, shape, loc=0., scale=1.):
+        super().__init__(shape, loc=loc, scale=scale)
+
+
+class StudentT(Prior):
+    _dist = td.StudentT
+
+    def __init__(self, shape, loc=0., scale=1., df=3.):
+        super().__init__(shape, df=df, loc=loc, scale=scale)
+
+
+class Improper(Normal):
+    "a prior the kernel must NOT fuse: log_prob is overridden (prior/loc_scale.py:94-97)"
+
+    def log_prob(self):
+        return 0. * self.p.sum()
+
+
+class LearnedScaleNormal(Prior):
+    "a prior the kernel must NOT fuse: the scale is a Parameter (prior/empirical_bayes.py:24-29)"
+    _dist = td.Normal
+
+    def __init__(self, shape, loc=0., scale=1.):
+        super().__init__(shape, loc=loc, scale=nn.Parameter(torch.tensor(float(scale))))
+
+
+class PriorLinear(nn.Module):
+    "models/layers.py:5-18: a Linear layer whose weight and bias are Prior modules"
+
+    def __init__(self, weight_prior, bias_prior):
+        super().__init__()
+        self.weight_prior, self.bias_prior = weight_prior, bias_prior
+
+    def forward(self, x):
+        return F.linear(x, self.weight_prior(), self.bias_prior())
+
+
+class TinyClassifier(nn.Module):
+    """din -> width -> width -> dout MLP with priors, the shape of the reference's
+    ClassificationDenseNet (models/dense_nets.py:48-71) incl. std/sqrt(fan_in) scales."""
+
+    def __init__(self, din, dout, width, prior_w=Normal, prior_b=Normal, w_kw=None, extra_bn=False):
+        super().__init__()
+        w_kw = w_kw or {}
+        dims = [din, width, width, dout]
+        layers = []
+        for a, b in zip(dims[:-1], dims[1:]):
+            layers.append(PriorLinear(prior_w((b, a), 0., math.sqrt(2.) / math.sqrt(a), **w_kw),
+                                      prior_b((b,), 0., 1.)))
+            if b != dout:
+                if extra_bn:
+                    layers.append(nn.BatchNorm1d(b))      # parameters without a prior
+                layers.append(nn.ReLU())
+        self.net = nn.Sequential(*layers)
+
+    def priors(self):
+        return [m for m in self.modules() if isinstance(m, Prior)]
+
+    def log_prior(self):
+        return sum(m.log_prob() for m in self.priors())
+
+    def log_likelihood_avg(self, x, y):
+        return td.Categorical(logits=self.net(x)).log_prob(y).sum() / x.shape[0]
+
+    def split_potential_and_acc(self, x, y, eff_num_data):
+        loss = -self.log_likelihood_avg(x, y)
+        log_prior = self.log_prior()
+        potential_avg = loss - log_prior / eff_num_data
+        return loss, log_prior, potential_avg
+
+
+class GaussianTarget:
+    """N data points from N(mean, std^2 I) in D dims with a flat prior: the posterior
+    over the location is N(xbar, std^2/N) -- the target of the reference's
+    distribution-preservation tests (testing/test_sgld.py:13-59)."""
+
+    def __init__(self, N, D, mean, std, device, seed=0):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        self.N, self.D, self.std = N, D, std
+        self.x = (torch.randn(N, D, generator=g) * std + mean).to(device)
+        self.xbar = self.x.mean(0)
+        self.post_std = std / math.sqrt(N)
+
+    def potential_avg(self, theta):
+        "-(1/N) log p(x | theta) up to a constant"
+        return (0.5 * ((self.x - theta) / self.std) ** 2).sum() / self.N
