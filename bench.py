@@ -222,9 +222,9 @@ def make_chain(device, seed, sampler="SGLD", tag=WORKLOAD, fused_prior=False, **
         for i, t in enumerate(tensors):
             fg.set_prior(i, t["kind"], t["loc"], t["scale"], t["df"])
         fg.prior_fused = True
-    fg.G.normal_(0.0, 1e-3, generator=g)
     for p, v in zip(params, fg.g_views):
         p.grad = v
+        v.normal_(0.0, 1e-3, generator=g)      # segment by segment: the padding stays zero
     opt.sample_momentum()
     return opt, params, fg
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BNNP_LIB") or os.path.join(HERE, "_lib", "libbnnp.so")
 
 # ---- constants of include/bnnp.h (tests/test_abi.py checks them against the header)
-ABI_VERSION = 3
+ABI_VERSION = 4
 SEG_ALIGN = 32
 THREADS = 256
 UNROLL = 4
@@ -59,7 +59,7 @@ class BnnpLaunch(C.Structure):
         ("P", C.c_void_p), ("G", C.c_void_p), ("M", C.c_void_p),
         ("prev_p", C.c_void_p), ("prev_g", C.c_void_p), ("prev_m", C.c_void_p),
         ("replay_noise", C.c_void_p),
-        ("segs", C.c_void_p), ("chunk_seg", C.c_void_p), ("seg_state", C.c_void_p),
+        ("segs", C.c_void_p), ("chunk_seg", C.c_void_p), ("chunk_ids", C.c_void_p), ("seg_state", C.c_void_p),
         ("partials", C.c_void_p), ("tickets", C.c_void_p),
         ("nseg", C.c_int32), ("nchunks", C.c_int32),
         ("op", C.c_int32), ("phase", C.c_int32), ("noise", C.c_int32),

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS>()) bnnp_step_ke
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
-    const int chunk = blockIdx.x;
+    const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[blockIdx.x] : (int)blockIdx.x;
     const int seg = L.chunk_seg[chunk];
     const BnnpSegment sd = L.segs[seg];
     const int64_t cbase = (int64_t)(chunk - sd.first_chunk) * CHUNK;

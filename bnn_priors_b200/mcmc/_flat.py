@@ -143,8 +143,8 @@ class FlatGroup:
         self.table["first_chunk"], self.table["num_chunks"] = first, nch
         self.table_dev = torch.empty(self.table.nbytes, dtype=torch.uint8, device=dev)
         self._table_dirty = True
-        self.chunk_seg_dev = torch.from_numpy(np.ascontiguousarray(chunk_seg)).to(dev)
-        self._all_chunks = (self.chunk_seg_dev, self.nchunks)
+        self.chunk_seg_host = np.ascontiguousarray(chunk_seg)
+        self.chunk_seg_dev = torch.from_numpy(self.chunk_seg_host).to(dev)
 
         # flat arrays
         self.P = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -338,7 +338,7 @@ class FlatGroup:
         if self._table_dirty:
             self._upload_table()
         a = self.args
-        chunk_seg, nchunks = chunks if chunks is not None else self._all_chunks
+        chunk_ids, nchunks = chunks if chunks is not None else (None, self.nchunks)
         a.P, a.G = self.P.data_ptr(), self.G.data_ptr()
         a.M = self.M.data_ptr() if self.M is not None else None
         a.prev_p = self.prev_p.data_ptr() if self.prev_p is not None else None
@@ -350,7 +350,9 @@ class FlatGroup:
             a.replay_noise = self.replay.data_ptr()
         else:
             a.replay_noise = None
-        a.segs, a.chunk_seg = self.table_dev.data_ptr(), chunk_seg.data_ptr()
+        a.segs, a.chunk_seg = self.table_dev.data_ptr(), self.chunk_seg_dev.data_ptr()
+        a.chunk_ids = chunk_ids.data_ptr() if chunk_ids is not None else None
+        self._chunk_ids_keepalive = chunk_ids
         a.seg_state, a.partials, a.tickets = self.state_dev.data_ptr(), self.partials.data_ptr(), self.tickets.data_ptr()
         a.nseg, a.nchunks = self.nseg, nchunks
         a.op, a.phase, a.noise, a.flags = op, phase, noise, flags
@@ -381,14 +383,14 @@ class FlatGroup:
         self.launches += 1
 
     def chunks_without(self, missing: Sequence[int]):
-        """Chunk list that skips the segments in `missing` (raise_on_no_grad=False)."""
+        """(device list of chunk indices, count) that skips the segments in `missing`
+        (raise_on_no_grad=False, sgld.py:96-101); None if nothing is left."""
         keep = np.ones(self.nseg, dtype=bool)
         keep[list(missing)] = False
-        cs = self._all_chunks[0].cpu().numpy()
-        sel = np.ascontiguousarray(cs[keep[cs]])
-        if sel.size == 0:
+        ids = np.ascontiguousarray(np.nonzero(keep[self.chunk_seg_host])[0].astype(np.int32))
+        if ids.size == 0:
             return None
-        return torch.from_numpy(sel).to(self.device), int(sel.size)
+        return torch.from_numpy(ids).to(self.device), int(ids.size)
 
     def take_noise_mode(self, needs_noise: bool) -> int:
         if not needs_noise:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BNNP_ABI_VERSION 3
+#define BNNP_ABI_VERSION 4
 
 #define BNNP_SEG_ALIGN 32      /* floats: every segment starts on a 128-byte line */
 #ifndef BNNP_THREADS
@@ -130,7 +130,10 @@ typedef struct BnnpLaunch {
     float* prev_m;
     const float* replay_noise; /* flat [total], BNNP_NOISE_REPLAY                   */
     const BnnpSegment* segs;   /* [nseg]                                            */
-    const int32_t* chunk_seg;  /* [nchunks]: segment of every chunk                 */
+    const int32_t* chunk_seg;  /* [all chunks]: segment of every chunk              */
+    const int32_t* chunk_ids;  /* null: process chunks 0..nchunks-1; else [nchunks]
+                                  chunk indices, whole segments only (used to skip
+                                  tensors without a gradient, sgld.py:96-101)       */
     double* seg_state;         /* [nseg][BNNP_STATE_STRIDE]                         */
     double* partials;          /* scratch [nchunks][BNNP_NRED]                      */
     uint32_t* tickets;         /* [nseg], zero-initialised once                     */

@@ -23,9 +23,9 @@ def make(sampler, seed=0, **hp):
     opt = getattr(mcmc, sampler)(params, **hp, seed=seed)
     (fg,) = opt.flat_groups
     assert fg.n_params == 25124842 and fg.nseg == 54
-    fg.G.normal_(0.0, 1e-3, generator=g)
     for p, v in zip(params, fg.g_views):
         p.grad = v
+    new_grads(fg, 1000 + seed)
     return opt, params, fg
 
 

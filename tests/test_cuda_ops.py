@@ -92,7 +92,13 @@ class Pair:
                 if want is None or (isinstance(want, float) and math.isnan(want)):
                     continue
                 got = st[k]
-                assert abs(got - want) <= 2e-5 * max(abs(want), 1e-3), (k, got, want, seg.p.size)
+                scale = 1e-3
+                if k in ("delta_energy", "prev_new_momentum_delta") and seg.m is not None:
+                    # running sums of signed terms c_gm * g.m: judge against one term's size
+                    g64, m64 = seg.g.astype(np.float64), seg.m.astype(np.float64)
+                    scale = abs(self.chain.group.derived.get("bhn", 1.0)) * seg.preconditioner * \
+                        math.sqrt(float(g64 @ g64) * float(m64 @ m64)) + 1e-3
+                assert abs(got - want) <= 2e-5 * max(abs(want), scale), (k, got, want, seg.p.size)
 
 
 HP = dict(lr=2e-3, num_data=40.0, momentum=0.9, temperature=0.7)
@@ -349,7 +355,7 @@ def test_views_survive_zero_grad_load_state_dict_and_schedulers():
     mcmc = _mcmc()
     lin = torch.nn.Linear(64, 32).to(DEV)
     ps = list(lin.parameters())
-    opt = mcmc.SGLD(ps, lr=0.5, num_data=1, momentum=0.9, temperature=0.0)
+    opt = mcmc.SGLD(ps, lr=1e-3, num_data=1, momentum=0.9, temperature=0.0)
     (fg,) = opt.flat_groups
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 0.5 ** s)       # inference.py:96-101
     opt.sample_momentum()
@@ -363,7 +369,7 @@ def test_views_survive_zero_grad_load_state_dict_and_schedulers():
         assert all(p.data_ptr() == v.data_ptr() for p, v in zip(ps, fg.p_views))
         opt.step(calc_metrics=False)
         sched.step()
-        assert opt.param_groups[0]["lr"] == pytest.approx(0.5 * 0.5 ** (it + 1))
+        assert opt.param_groups[0]["lr"] == pytest.approx(1e-3 * 0.5 ** (it + 1))
     # a parameter whose storage was swapped (Prior.sample(), prior/base.py:68-70) is re-adopted
     with torch.no_grad():
         ps[0].data = torch.full_like(ps[0], 3.0)
@@ -371,7 +377,7 @@ def test_views_survive_zero_grad_load_state_dict_and_schedulers():
     lin(x).sum().backward()
     opt.step(calc_metrics=False)
     assert ps[0].data_ptr() == fg.p_views[0].data_ptr()
-    assert abs(float(ps[0].mean()) - 3.0) < 1.0
+    assert abs(float(ps[0].detach().mean()) - 3.0) < 0.1
 
 
 def test_two_param_groups():

@@ -110,12 +110,14 @@ def test_verlet_distribution_preservation(n_vars=50, n_dim=1000, n_samples=200, 
     torch.manual_seed(145)
     mean, std, temperature = 1., 2., 3 / 4
     model = gaussian_model(n_vars, n_dim, mean, std, temperature)
-    sgld = VerletSGLD(model.parameters(), lr=1 / 32, num_data=1, momentum=0.9, temperature=temperature)
+    # lr: the reference uses 1/32, where (oracle run, same sizes) the acceptance is 0.996 and
+    # nothing is ever rejected; 3/8 gives ~0.78 and ~16 rejections in 50 decisions
+    sgld = VerletSGLD(model.parameters(), lr=3 / 8, num_data=1, momentum=0.9, temperature=temperature)
     for _, state in sgld.state.items():
         state['preconditioner'] = (torch.rand(()).item() + 0.2) / math.sqrt(4)
     sgld.sample_momentum()
     acc, n_rej = _mh_loop(sgld, model, n_samples, mh_freq, hmc=False)
-    assert acc > 0.6                   # "Was 0.73 at commit 56988f7"
+    assert acc > 0.6
     assert 0 < n_rej < n_samples // mh_freq
     parameters, kinetic, config = _collect(sgld, n_vars, n_dim)
     _check_distribution(parameters, {"configurational": config, "kinetic": kinetic}, mean, std, temperature, n_dim)
@@ -127,11 +129,12 @@ def test_hmc_distribution_preservation(n_vars=50, n_dim=1000, n_samples=200, mh_
     torch.manual_seed(122)
     mean, std = 1., 2.
     model = gaussian_model(n_vars, n_dim, mean, std, 1.)
-    sgld = HMC(model.parameters(), lr=1 / 32, num_data=1)
+    # lr 1/4 instead of the reference's 1/32 for the same reason as above (oracle: 0.72, ~10 rejections)
+    sgld = HMC(model.parameters(), lr=1 / 4, num_data=1)
     for _, state in sgld.state.items():
         state['preconditioner'] = (torch.rand(()).item() + 0.2) / math.sqrt(std)
     acc, n_rej = _mh_loop(sgld, model, n_samples, mh_freq, hmc=True)
-    assert acc > 0.6                   # "Was 0.65 at commit 56988f7"
+    assert acc > 0.5 and 0 < n_rej < n_samples // mh_freq
     parameters, kinetic, config = _collect(sgld, n_vars, n_dim)
     _check_distribution(parameters, {"configurational": config, "kinetic": kinetic}, mean, std, 1., n_dim)
 
