@@ -1,0 +1,36 @@
+"""bnn_priors_b200.overlay against the live reference (build container only): after
+install() the reference's runner modules construct the B200 sampler classes."""
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "bnn_priors")), reason="no reference checkout here")
+def test_overlay_rebinds_the_reference_samplers():
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, os.path.join(HERE, "golden", "_shims"))
+    sys.path.insert(0, REFERENCE)
+    try:
+        import bnn_priors.mcmc as ref_mcmc
+        from bnn_priors import inference, inference_reject
+        from bnn_priors_b200 import mcmc as fast, overlay
+        original = ref_mcmc.VerletSGLD
+        assert original is not fast.VerletSGLD
+        overlay.install()
+        try:
+            # what the runners will construct (inference.py:89-94, inference_reject.py:12-16)
+            assert inference.mcmc.SGLD is fast.SGLD
+            assert inference.mcmc.HMC is fast.HMC
+            assert inference_reject.mcmc.VerletSGLD is fast.VerletSGLD
+            from bnn_priors.mcmc.sgld import SGLD as by_submodule
+            assert by_submodule is fast.SGLD
+        finally:
+            overlay.uninstall()
+        assert ref_mcmc.VerletSGLD is original and inference.mcmc.SGLD is not fast.SGLD
+    finally:
+        sys.path.remove(REFERENCE)
+        sys.path.remove(os.path.join(HERE, "golden", "_shims"))
