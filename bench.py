@@ -285,12 +285,14 @@ def run_gpu(args):
 
     # ---- end to end: gradient from pinned host memory in, diagnostics out, every step
     E = max(3, min(K, 30))
-    host_g = [torch.empty(p.shape, dtype=torch.float32).normal_(0, 1e-3).pin_memory() for p in params]
+    # the step's input (the gradient, in the chain's flat layout) lives in pinned host memory
+    host_g = torch.zeros(fg.total, dtype=torch.float32).pin_memory()
+    for o, k in zip(fg.off, fg.numel):
+        host_g[o:o + k].normal_(0, 1e-3)
     p0 = params[0]
 
     def e2e_step():
-        for p, hg in zip(params, host_g):
-            p.grad.copy_(hg, non_blocking=True)
+        fg.G.copy_(host_g, non_blocking=True)         # H2D, 4 bytes per parameter
         opt.step(calc_metrics=True)
         return opt.state[p0]["est_temperature"]      # D2H of the segment-state array + sync
 
@@ -309,7 +311,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     sampler.stop()
-    h2d = 4 * n
+    h2d = 4 * fg.total
     d2h = fg.nseg * N.STATE_STRIDE * 8
 
     # ---- other transitions of the path (kernel time, same chain size), for context

@@ -43,10 +43,9 @@ class HMC(VerletSGLD):
         "hmc.py:32-33: .5 * dot(momentum, momentum) of the momentum now stored"
         return .5 * float(fg.fetch()[i, N.S_SUM_MM])
 
-    def _update_group_fn(self, g):
-        # Ensure momentum and temperature are correct at every step
-        # No matter what modifications are done before `self.step`.
-        super()._update_group_fn(g)
+    def _update_group_fn(self, g, *, phase=N.PHASE_MID):
+        # whatever a runner or scheduler wrote into the group, HMC is a = 1, T = 1 (hmc.py:35-39)
+        super()._update_group_fn(g, phase=phase)
         assert g['momentum'] == 1. and g['temperature'] == 1.
 
     def _step_fn(self, group, fg: FlatGroup, chunks, is_initial=False, is_final=False,

@@ -20,14 +20,9 @@ from .sgld import SGLD, dot  # noqa: F401  (dot re-exported like the reference)
 
 
 class VerletSGLD(SGLD):
-    """SGLD with momentum, preconditioning and diagnostics from Wenzel et al. 2020.
-    Uses Verlet integration instead of Euler symplectic integration.
-
-    The contribution from the Verlet integration to the acceptance probability
-    is neutral (multiply by 1), because it is perfectly time-reversible.
-
-    Args: see `SGLD` (the reference's signature, mcmc/sgld.py:31-34).
-    """
+    """Gradient-guided Monte Carlo: underdamped Langevin dynamics split as OBABO, with the
+    energy bookkeeping that makes a Metropolis-Hastings correction possible.  Same arguments
+    as `SGLD` (the reference's signature, mcmc/sgld.py:31-34)."""
     _OP = N.OP_VERLET
 
     # ------------------------------------------------------------------ energies
@@ -47,10 +42,10 @@ class VerletSGLD(SGLD):
             fg.reduce_now(1.0 / group['num_data'] if fg.prior_fused else 0.0)
 
     def delta_energy(self, prev_potential: float, potential: float) -> float:
-        "Calculates the difference in energy since the last `initial_step` and now."
+        """Energy difference between the last `initial_step` and now (verlet_sgld.py:27-42):
+        per-tensor running sums from the device + point energies + N (U - U_prev)."""
         num_data = self.param_groups[0]['num_data']
-        assert all(g['num_data'] == num_data for g in self.param_groups),\
-            "unclear which `num_data` to use"
+        assert all(g['num_data'] == num_data for g in self.param_groups), "unclear which `num_data` to use"
         delta_energy = 0.
         for group, fg in zip(self.param_groups, self._flat):
             self._refresh_sums(group, fg)
@@ -79,15 +74,13 @@ class VerletSGLD(SGLD):
 
     @torch.no_grad()
     def maybe_reject(self, delta_energy: float) -> (bool, float):
-        "Maybe reject the current parameters, based on the difference in energy"
+        """Metropolis-Hastings test (verlet_sgld.py:49-70).  The uniform comes from torch's CPU
+        generator with the same single draw as the reference, so host RNG streams stay aligned;
+        a rejection restores P, G, M from the snapshot with one device-to-device kernel."""
         temperature = self.param_groups[0]['temperature']
-        assert all(g['temperature'] == temperature for g in self.param_groups),\
-            "unclear which `temperature` to use"
-
+        assert all(g['temperature'] == temperature for g in self.param_groups), "unclear which `temperature` to use"
         if temperature == 0.0:
-            return False, 0.  # Never reject
-
-        # rand() > min(1., exp(-delta_energy / temperature))
+            return False, 0.  # descent phase: never reject
         log_accept_prob = -delta_energy / temperature
         reject = (math.log(torch.rand(()).item()) > log_accept_prob)
         if reject:
@@ -97,64 +90,52 @@ class VerletSGLD(SGLD):
         return reject, log_accept_prob
 
     # ------------------------------------------------------------------ transitions
+    # OBABO splitting: an `initial_step` (theta(n), m(n) -> theta(n+1), u(n+1)), any number of
+    # `step`s (theta(n), u(n) -> theta(n+1), u(n+1)) and a `final_step` (theta(n), u(n) ->
+    # theta(n), m(n)), where u = sqrt(a) m + noise is the half-updated momentum.  The three
+    # differ only in the scalars below (verlet_sgld.py:96-101, :129-134, :138-146).
+    @staticmethod
+    def _phase_scalars(a, temperature, phase):
+        "(mom_decay, grad_v, noise_std) of a transition for momentum parameter a"
+        if phase == N.PHASE_MID:
+            return a, 1 + a, math.sqrt((1 - a**2) * temperature)
+        root_a = math.sqrt(a)
+        half_noise = math.sqrt((1 - a) * temperature)
+        return root_a, (1. if phase == N.PHASE_INITIAL else root_a), half_noise
+
+    def _update_group_fn(self, g, *, phase=N.PHASE_MID):
+        "derived entries of a param group, from its CURRENT lr / num_data / momentum / temperature"
+        g['b^2h^2'] = g['lr'] / g['num_data']
+        g['bh'] = math.sqrt(g['b^2h^2'])
+        g['bhn'] = math.sqrt(g['lr'] * g['num_data'])
+        g['mom_decay'], g['grad_v'], g['noise_std'] = self._phase_scalars(
+            g['momentum'], g['temperature'], phase)
+
+    def _transition(self, phase, closure, **step_kwargs):
+        if phase != N.PHASE_MID:
+            # keep a `torch.optim.lr_scheduler` happy (verlet_sgld.py:95,128)
+            self._step_count = getattr(self, '_step_count', 0) + 1
+        return self._step_internal(lambda g: self._update_group_fn(g, phase=phase), self._step_fn, closure,
+                                   is_initial=(phase == N.PHASE_INITIAL), is_final=(phase == N.PHASE_FINAL),
+                                   **step_kwargs)
+
     @torch.no_grad()
     def initial_step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
                      save_state=True, calc_metrics=True):
-        """The initial transition for the Verlet integrator.
-        θ(n), m(n) -> θ(n+1), u(n+1)
-
-        u(n) is not the momentum, rather, it is
-        u(n) = sqrt(b)*m(n) - gradient of parameters
-        """
-        # keep a `torch.optim.lr_scheduler` happy
-        self._step_count = getattr(self, '_step_count', 0) + 1
-
-        def update_group_fn(g):
-            self._update_group_fn(g)
-            a = g['momentum']
-            g['mom_decay'] = math.sqrt(a)
-            g['grad_v'] = 1.
-            g['noise_std'] = math.sqrt((1 - a) * g['temperature'])
-        return self._step_internal(update_group_fn, self._step_fn, closure,
-                                   is_initial=True, save_state=save_state,
-                                   calc_metrics=calc_metrics)
+        "First transition after (re)sampling / accepting: optionally snapshots the state for a rejection."
+        return self._transition(N.PHASE_INITIAL, closure, save_state=save_state, calc_metrics=calc_metrics)
 
     @torch.no_grad()
     def step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
              calc_metrics=True):
-        """An intermediate transition for the Verlet integrator.
-        θ(n), u(n) -> θ(n+1), u(n+1)
-        """
-        return self._step_internal(self._update_group_fn, self._step_fn,
-                                   closure, calc_metrics=calc_metrics)
+        "An intermediate transition."
+        return self._transition(N.PHASE_MID, closure, calc_metrics=calc_metrics)
 
     @torch.no_grad()
     def final_step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
                    calc_metrics=True):
-        """The final transition for the Verlet integrator
-        θ(n), u(n) -> θ(n), m(n)
-        """
-        # keep a `torch.optim.lr_scheduler` happy
-        self._step_count = getattr(self, '_step_count', 0) + 1
-
-        def update_group_fn(g):
-            self._update_group_fn(g)
-            a = g['momentum']
-            g['mom_decay'] = math.sqrt(a)
-            g['grad_v'] = g['mom_decay']
-            g['noise_std'] = math.sqrt((1 - a) * g['temperature'])
-        return self._step_internal(update_group_fn, self._step_fn, closure,
-                                   is_final=True, calc_metrics=calc_metrics)
-
-    def _update_group_fn(self, g):
-        g['b^2h^2'] = g['lr'] / g['num_data']
-        g['bh'] = math.sqrt(g['b^2h^2'])
-        g['bhn'] = math.sqrt(g['lr'] * g['num_data'])
-
-        a = g['momentum']
-        g['mom_decay'] = a
-        g['grad_v'] = 1 + a
-        g['noise_std'] = math.sqrt((1 - a**2) * g['temperature'])
+        "Last transition before the M-H test: completes the momentum, leaves the parameters where they are."
+        return self._transition(N.PHASE_FINAL, closure, calc_metrics=calc_metrics)
 
     def _phase(self, is_initial, is_final):
         return N.PHASE_INITIAL if is_initial else (N.PHASE_FINAL if is_final else N.PHASE_MID)
