@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BNNP_LIB") or os.path.join(HERE, "_lib", "libbnnp.so")
 
 # ---- constants of include/bnnp.h (tests/test_abi.py checks them against the header)
-ABI_VERSION = 4
+ABI_VERSION = 5
 SEG_ALIGN = 32
 THREADS = 256
 UNROLL = 4
@@ -54,25 +54,34 @@ SEGMENT_DTYPE = np.dtype([
 assert SEGMENT_DTYPE.itemsize == 48
 
 
+class BnnpEpilogue(C.Structure):
+    _fields_ = [
+        ("valid", C.c_int32), ("op", C.c_int32), ("phase", C.c_int32), ("flags", C.c_uint32),
+        ("parity", C.c_int32), ("reserved", C.c_int32), ("call", C.c_uint64),
+        ("c_gm_base", C.c_double), ("curv_base", C.c_double), ("rms_alpha", C.c_double),
+    ]
+
+
 class BnnpLaunch(C.Structure):
     _fields_ = [
         ("P", C.c_void_p), ("G", C.c_void_p), ("M", C.c_void_p),
         ("prev_p", C.c_void_p), ("prev_g", C.c_void_p), ("prev_m", C.c_void_p),
         ("replay_noise", C.c_void_p),
         ("segs", C.c_void_p), ("chunk_seg", C.c_void_p), ("chunk_ids", C.c_void_p), ("seg_state", C.c_void_p),
-        ("partials", C.c_void_p), ("tickets", C.c_void_p),
-        ("nseg", C.c_int32), ("nchunks", C.c_int32),
+        ("partials", C.c_void_p), ("stamps", C.c_void_p),
+        ("nseg", C.c_int32), ("nchunks", C.c_int32), ("nchunks_total", C.c_int32), ("parity", C.c_int32),
         ("op", C.c_int32), ("phase", C.c_int32), ("noise", C.c_int32),
         ("flags", C.c_uint32), ("key0", C.c_uint32), ("key1", C.c_uint32),
         ("call", C.c_uint64),
         ("cm", C.c_double), ("cg", C.c_double), ("cn", C.c_double), ("cp", C.c_double),
         ("inv_num_data", C.c_double), ("grad_max", C.c_double),
         ("c_gm_base", C.c_double), ("curv_base", C.c_double), ("rms_alpha", C.c_double),
+        ("pending", BnnpEpilogue),
     ]
 
 
 EXPORTS = ("bnnp_abi_version", "bnnp_last_error", "bnnp_device_info", "bnnp_max_ctas_per_sm",
-           "bnnp_plan_layout", "bnnp_launch", "bnnp_rollback")
+           "bnnp_plan_layout", "bnnp_launch", "bnnp_finalize", "bnnp_rollback", "bnnp_probe_stream")
 
 
 class BnnpError(RuntimeError):
@@ -99,7 +108,9 @@ def lib() -> C.CDLL:
     l.bnnp_plan_layout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p]
     l.bnnp_launch.argtypes = [C.POINTER(BnnpLaunch), C.c_void_p]
+    l.bnnp_finalize.argtypes = [C.POINTER(BnnpLaunch), C.c_void_p]
     l.bnnp_rollback.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
+    l.bnnp_probe_stream.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
     for name in EXPORTS:
         getattr(l, name)          # AttributeError if a symbol is missing
     if l.bnnp_abi_version() != ABI_VERSION:

@@ -8,11 +8,17 @@
 // gradient (prior/loc_scale.py:34-77)  ->  noise from an in-register Philox4x32-10
 // + Box-Muller (or a replay buffer for parity tests)  ->  momentum and parameter
 // update  ->  128-bit stores of p', m' (and the verlet_sgld.py:72-83 snapshot)  ->
-// eight dot products per chunk, reduced warp -> CTA -> segment in a fixed order.
-// The last CTA of every segment (ticket counter) folds the chunk partials in fp64
-// and applies the sampler's scalar bookkeeping (delta_energy,
-// prev_new_momentum_delta, est_temperature, est_config_temp, square_avg mean) on
-// the device, so the host never has to synchronise unless it wants a scalar.
+// eight dot products per chunk, reduced warp -> CTA in a fixed order and published
+// as one fp64 partial record per chunk with plain stores (no fence, no atomics: a
+// fence + ticket at the end of every CTA cost 9 us of an 88 us step,
+// profiles/r01_tile_sweep.md).  The per-segment fold of those records and the
+// sampler's scalar bookkeeping (delta_energy, prev_new_momentum_delta,
+// est_temperature, est_config_temp, square_avg mean) are DEFERRED: the launch that
+// follows carries the previous launch's epilogue parameters (BnnpLaunch.pending) and
+// CTA j applies them for segment j before its own work; when the
+// host wants a scalar, bnnp_finalize does the same in a tiny launch of its own.
+// Either way it happens on the device, in a fixed order (bit-reproducible), and a
+// step never synchronises the host.
 //
 // The path is HBM-bound elementwise work: no tensor cores, no shared-memory tiles;
 // what matters is coalesced 16-byte accesses, enough loads in flight per SM and a
@@ -248,6 +254,96 @@ __device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c,
     }
 }
 
+__host__ __device__ inline int sums_needed(int op, uint32_t flags) {
+    if (flags & (BNNP_F_CALC_METRICS | BNNP_F_ALL_SUMS)) return SUMS_ALL;
+    if (op == BNNP_OP_SAMPLE_MOMENTUM || op == BNNP_OP_REDUCE) return SUMS_ALL;
+    return op == BNNP_OP_VERLET ? SUMS_VERLET : SUMS_MIN;
+}
+
+// The reference's per-tensor scalar bookkeeping for one segment and one launch `E`,
+// applied to the segment-state array (fp64) from the eight folded sums `r`.
+__device__ void segment_epilogue(const BnnpEpilogue& E, double* seg_state, const BnnpSegment& sd, int seg,
+                                 const double* r) {
+    const uint32_t flags = E.flags;
+    const int sums = sums_needed(E.op, flags);
+    const double gm_old = r[R_GM_OLD], gm_new = r[R_GM_NEW];
+    const double mm_old = r[R_MM_OLD], mm_new = r[R_MM_NEW];
+    const double pg = r[R_PG], gg = r[R_GG];
+    double* st = seg_state + (int64_t)seg * BNNP_STATE_STRIDE;
+    const double M = sd.precond;
+    const bool metrics = (flags & BNNP_F_CALC_METRICS) != 0;
+
+    if (sums >= SUMS_VERLET) {
+        st[BNNP_S_GM_OLD] = gm_old;
+        st[BNNP_S_GM_NEW] = gm_new;
+    }
+    if (sums == SUMS_ALL) {
+        st[BNNP_S_MM_OLD] = mm_old;
+        st[BNNP_S_MM_NEW] = mm_new;
+    }
+    if (flags & BNNP_F_READ_G) {
+        st[BNNP_S_SUM_GG] = gg;
+        st[BNNP_S_NONFINITE] = (r[R_NONFINITE] == 0.0) ? 0.0 : 1.0;
+    }
+    if (E.op == BNNP_OP_VERLET) {
+        const double c_gm = E.c_gm_base * M;                       // verlet_sgld.py:170
+        if (E.phase == BNNP_PHASE_INITIAL) {
+            st[BNNP_S_DELTA_ENERGY] = -((M * M) * E.curv_base * gg);   // :171-172 with :44-47
+        } else {
+            double de = st[BNNP_S_DELTA_ENERGY];
+            de += st[BNNP_S_PREV_NEW_MOM];                          // :174
+            de += c_gm * gm_old;                                    // :175
+            st[BNNP_S_DELTA_ENERGY] = de;
+        }
+        st[BNNP_S_PREV_NEW_MOM] = c_gm * gm_new;                    // :176
+        if (metrics) st[BNNP_S_EST_MM] = (E.phase == BNNP_PHASE_FINAL) ? mm_new : mm_old;   // :181-187
+    } else if (E.op == BNNP_OP_HMC) {
+        if (E.phase == BNNP_PHASE_INITIAL && sums == SUMS_ALL) st[BNNP_S_DELTA_ENERGY] = -0.5 * mm_old;   // hmc.py:50-53
+        if (metrics) st[BNNP_S_EST_MM] = (E.phase == BNNP_PHASE_FINAL) ? mm_new : mm_old;   // :55,60,72
+    } else if (E.op == BNNP_OP_SGLD) {
+        if (metrics) st[BNNP_S_EST_MM] = mm_old;                    // sgld.py:127,137
+    }
+    if (metrics && E.op <= BNNP_OP_HMC) st[BNNP_S_EST_PG] = pg;     // sgld.py:146
+    if (sums == SUMS_ALL) {
+        if (flags & BNNP_F_WRITE_M) st[BNNP_S_SUM_MM] = mm_new;
+        else if (flags & BNNP_F_READ_M) st[BNNP_S_SUM_MM] = mm_old;
+    }
+    if (flags & BNNP_F_UPDATE_SQ)                                   // sgld.py:153-154, through its mean
+        st[BNNP_S_SQ_MEAN] = E.rms_alpha * st[BNNP_S_SQ_MEAN] + (1.0 - E.rms_alpha) * (gg / (double)sd.numel);
+    if (flags & BNNP_F_LOG_PRIOR)
+        st[BNNP_S_LOG_PRIOR] = r[R_LOGP] + (double)sd.numel * log_prior_const(sd);
+    st[BNNP_S_LAUNCHES] += 1.0;
+}
+
+// CTA-wide: fold the partial records launch `L.pending` left for segment `seg` (one warp
+// per sum, lanes over the chunks, fp64, fixed order) and apply its epilogue.  A segment
+// the pending launch skipped carries an older stamp and is left alone.
+__device__ void apply_pending(const BnnpLaunch& L, const BnnpSegment& sd, int seg, double* s_sum) {
+    const BnnpEpilogue& E = L.pending;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t rec0 = (int64_t)E.parity * L.nchunks_total + sd.first_chunk;
+    if (L.stamps[rec0] != E.call + 1) return;     // uniform over the CTA
+    for (int k = warp; k < BNNP_NRED; k += NWARPS) {
+        const double* base = L.partials + rec0 * BNNP_NRED + k;
+        // eight independent running sums per lane keep eight L2 loads in flight; they are
+        // combined in a fixed order, so the result does not depend on timing
+        double s[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+        for (int ch = lane; ch < sd.num_chunks; ch += 32 * 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = ch + 32 * j;
+                if (c < sd.num_chunks) s[j] += ld_cg_f64(base + (int64_t)c * BNNP_NRED);
+            }
+        }
+        double t = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+        t = warp_sum_f64(t);
+        if (lane == 0) s_sum[k] = t;
+    }
+    __syncthreads();
+    if (tid == 0) segment_epilogue(E, L.seg_state, sd, seg, s_sum);
+    __syncthreads();   // s_sum is reused by the caller
+}
+
 struct ChunkCtx {
     int64_t fbase;   // flat index of the chunk's first float
     int rem;         // valid floats in this chunk
@@ -299,12 +395,14 @@ constexpr int min_ctas() {
 template <int NOISE, bool PRIOR, bool NOISE_FIRST, int SUMS>
 __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS>()) bnnp_step_kernel(const BnnpLaunch L) {
     __shared__ double s_red[NWARPS][BNNP_NRED];
-    __shared__ int s_last;
 
     const int tid = threadIdx.x;
     const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[blockIdx.x] : (int)blockIdx.x;
     const int seg = L.chunk_seg[chunk];
     const BnnpSegment sd = L.segs[seg];
+    // the previous launch's bookkeeping: segment j is handled by CTA j, i.e. by the CTAs that
+    // start first, so the few microseconds it takes are absorbed at the front of the launch
+    if (L.pending.valid && (int)blockIdx.x < L.nseg) apply_pending(L, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
     const int64_t cbase = (int64_t)(chunk - sd.first_chunk) * CHUNK;
     const int64_t left = sd.numel - cbase;
     ChunkCtx cx;
@@ -382,77 +480,16 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS>()) bnnp_step_ke
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < NWARPS; ++w) s += s_red[w][tid];
-        L.partials[(int64_t)chunk * BNNP_NRED + tid] = s;
-        __threadfence();
+        L.partials[((int64_t)L.parity * L.nchunks_total + chunk) * BNNP_NRED + tid] = s;
     }
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t ticket = atomicAdd(L.tickets + seg, 1u);
-        s_last = (ticket == (uint32_t)(sd.num_chunks - 1));
-    }
-    __syncthreads();
-    if (!s_last) return;
+    if (tid == 0) L.stamps[(int64_t)L.parity * L.nchunks_total + chunk] = L.call + 1;   // "this launch wrote it"
+}
 
-    // ---- segment epilogue, run by the last CTA of this segment to finish
-    __threadfence();
-    for (int k = warp; k < BNNP_NRED; k += NWARPS) {   // one warp per partial sum, fixed order
-        const double* base = L.partials + (int64_t)sd.first_chunk * BNNP_NRED + k;
-        double s = 0.0;
-        for (int ch = lane; ch < sd.num_chunks; ch += 32) s += ld_cg_f64(base + (int64_t)ch * BNNP_NRED);
-        s = warp_sum_f64(s);
-        if (lane == 0) s_red[0][k] = s;
-    }
-    __syncthreads();
-    if (tid != 0) return;
-
-    const double gm_old = s_red[0][R_GM_OLD], gm_new = s_red[0][R_GM_NEW];
-    const double mm_old = s_red[0][R_MM_OLD], mm_new = s_red[0][R_MM_NEW];
-    const double pg = s_red[0][R_PG], gg = s_red[0][R_GG];
-    double* st = L.seg_state + (int64_t)seg * BNNP_STATE_STRIDE;
-    const double M = sd.precond;
-    const bool metrics = (flags & BNNP_F_CALC_METRICS) && SUMS == SUMS_ALL;
-
-    if (SUMS >= SUMS_VERLET) {
-        st[BNNP_S_GM_OLD] = gm_old;
-        st[BNNP_S_GM_NEW] = gm_new;
-    }
-    if (SUMS == SUMS_ALL) {
-        st[BNNP_S_MM_OLD] = mm_old;
-        st[BNNP_S_MM_NEW] = mm_new;
-    }
-    if (flags & BNNP_F_READ_G) {
-        st[BNNP_S_SUM_GG] = gg;
-        st[BNNP_S_NONFINITE] = (s_red[0][R_NONFINITE] == 0.0) ? 0.0 : 1.0;
-    }
-    if (L.op == BNNP_OP_VERLET && SUMS >= SUMS_VERLET) {
-        const double c_gm = L.c_gm_base * M;                       // verlet_sgld.py:170
-        if (L.phase == BNNP_PHASE_INITIAL) {
-            st[BNNP_S_DELTA_ENERGY] = -((M * M) * L.curv_base * gg);   // :171-172 with :44-47
-        } else {
-            double de = st[BNNP_S_DELTA_ENERGY];
-            de += st[BNNP_S_PREV_NEW_MOM];                          // :174
-            de += c_gm * gm_old;                                    // :175
-            st[BNNP_S_DELTA_ENERGY] = de;
-        }
-        st[BNNP_S_PREV_NEW_MOM] = c_gm * gm_new;                    // :176
-        if (metrics) st[BNNP_S_EST_MM] = (L.phase == BNNP_PHASE_FINAL) ? mm_new : mm_old;   // :181-187
-    } else if (L.op == BNNP_OP_HMC) {
-        if (L.phase == BNNP_PHASE_INITIAL && SUMS == SUMS_ALL) st[BNNP_S_DELTA_ENERGY] = -0.5 * mm_old;   // hmc.py:50-53
-        if (metrics) st[BNNP_S_EST_MM] = (L.phase == BNNP_PHASE_FINAL) ? mm_new : mm_old;   // :55,60,72
-    } else if (L.op == BNNP_OP_SGLD) {
-        if (metrics) st[BNNP_S_EST_MM] = mm_old;                    // sgld.py:127,137
-    }
-    if (metrics && L.op <= BNNP_OP_HMC) st[BNNP_S_EST_PG] = pg;     // sgld.py:146
-    if (SUMS == SUMS_ALL) {
-        if (flags & BNNP_F_WRITE_M) st[BNNP_S_SUM_MM] = mm_new;
-        else if (flags & BNNP_F_READ_M) st[BNNP_S_SUM_MM] = mm_old;
-    }
-    if (flags & BNNP_F_UPDATE_SQ)                                   // sgld.py:153-154, through its mean
-        st[BNNP_S_SQ_MEAN] = L.rms_alpha * st[BNNP_S_SQ_MEAN] + (1.0 - L.rms_alpha) * (gg / (double)sd.numel);
-    if (PRIOR && (flags & BNNP_F_LOG_PRIOR))
-        st[BNNP_S_LOG_PRIOR] = s_red[0][R_LOGP] + (double)sd.numel * log_prior_const(sd);
-    st[BNNP_S_LAUNCHES] += 1.0;
-    L.tickets[seg] = 0u;   // ready for the next (stream-ordered) launch
+// bnnp_finalize: the pending epilogue of every segment, nothing else
+__global__ void __launch_bounds__(THREADS) bnnp_finalize_kernel(const BnnpLaunch L) {
+    __shared__ double s_red[BNNP_NRED];
+    const int seg = blockIdx.x;
+    apply_pending(L, L.segs[seg], seg, s_red);
 }
 
 // P,G,M <- prev_* : verlet_sgld.py:63-69
@@ -469,6 +506,37 @@ __global__ void __launch_bounds__(THREADS) bnnp_rollback_kernel(float* __restric
         st_f4(P + 4 * q, a);
         st_f4(G + 4 * q, b);
         if (pm != nullptr) st_f4(M + 4 * q, cc);
+    }
+}
+
+// Diagnostic: the bare access pattern of a step (read p, g, m; write p, m) with two FMAs
+// per element and nothing else -- the ceiling tools/tune_tiles.py compares the real kernel to.
+__global__ void __launch_bounds__(THREADS, BNNP_MIN_CTAS) bnnp_probe_stream_kernel(float* __restrict__ P,
+                                                                                   const float* __restrict__ G,
+                                                                                   float* __restrict__ M,
+                                                                                   int64_t nquads) {
+    const int64_t base = (int64_t)blockIdx.x * (THREADS * UNROLL) + threadIdx.x;
+    float4 p[UNROLL], g[UNROLL], m[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int64_t q = base + (int64_t)u * THREADS;
+        if (q < nquads) {
+            p[u] = ld_f4(P + 4 * q);
+            g[u] = ld_f4(G + 4 * q);
+            m[u] = ld_f4(M + 4 * q);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int64_t q = base + (int64_t)u * THREADS;
+        if (q < nquads) {
+            m[u].x = fmaf(0.5f, g[u].x, m[u].x); m[u].y = fmaf(0.5f, g[u].y, m[u].y);
+            m[u].z = fmaf(0.5f, g[u].z, m[u].z); m[u].w = fmaf(0.5f, g[u].w, m[u].w);
+            p[u].x = fmaf(0.5f, m[u].x, p[u].x); p[u].y = fmaf(0.5f, m[u].y, p[u].y);
+            p[u].z = fmaf(0.5f, m[u].z, p[u].z); p[u].w = fmaf(0.5f, m[u].w, p[u].w);
+            st_f4(P + 4 * q, p[u]);
+            st_f4(M + 4 * q, m[u]);
+        }
     }
 }
 
@@ -497,13 +565,6 @@ StepKernel pick_kernel(int noise, bool prior, bool noise_first, int sums) {
         case BNNP_NOISE_PHILOX: return pick_noise<BNNP_NOISE_PHILOX>(prior, noise_first, sums);
     }
     return nullptr;
-}
-
-// which dot products the epilogue of (op, flags) reads
-int sums_needed(int op, uint32_t flags) {
-    if (flags & (BNNP_F_CALC_METRICS | BNNP_F_ALL_SUMS)) return SUMS_ALL;
-    if (op == BNNP_OP_SAMPLE_MOMENTUM || op == BNNP_OP_REDUCE) return SUMS_ALL;
-    return op == BNNP_OP_VERLET ? SUMS_VERLET : SUMS_MIN;
 }
 
 bool misaligned(const void* p) { return ((uintptr_t)p & 15u) != 0; }
@@ -559,8 +620,16 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
     if (a == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: null args");
     if (a->nseg <= 0 || a->nchunks <= 0) return fail(BNNP_E_ARG, "bnnp_launch: empty chain");
     if (a->segs == nullptr || a->chunk_seg == nullptr || a->seg_state == nullptr || a->partials == nullptr ||
-        a->tickets == nullptr)
+        a->stamps == nullptr)
         return fail(BNNP_E_ARG, "bnnp_launch: null table pointer");
+    if (a->nchunks > a->nchunks_total || (a->chunk_ids == nullptr && a->nchunks != a->nchunks_total))
+        return fail(BNNP_E_ARG, "bnnp_launch: nchunks does not match the plan");
+    if ((a->parity | 1) != 1 || (a->pending.valid && (a->pending.parity | 1) != 1))
+        return fail(BNNP_E_ARG, "bnnp_launch: parity must be 0 or 1");
+    if (a->pending.valid && a->chunk_ids != nullptr)
+        return fail(BNNP_E_ARG, "bnnp_launch: a launch with chunk_ids cannot carry a pending epilogue; bnnp_finalize first");
+    if (a->pending.valid && a->pending.parity == a->parity)
+        return fail(BNNP_E_ARG, "bnnp_launch: this launch would overwrite the partial records of the pending one");
     if (a->op < BNNP_OP_SGLD || a->op > BNNP_OP_REDUCE) return fail(BNNP_E_ARG, "bnnp_launch: bad op");
     if (a->phase < BNNP_PHASE_INITIAL || a->phase > BNNP_PHASE_FINAL) return fail(BNNP_E_ARG, "bnnp_launch: bad phase");
     const uint32_t f = a->flags;
@@ -582,6 +651,29 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
     k<<<a->nchunks, THREADS, 0, (cudaStream_t)stream>>>(*a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "bnnp_step_kernel launch");
+    return 0;
+}
+
+int bnnp_finalize(const BnnpLaunch* a, void* stream) {
+    if (a == nullptr) return fail(BNNP_E_ARG, "bnnp_finalize: null args");
+    if (!a->pending.valid) return 0;
+    if (a->nseg <= 0 || a->segs == nullptr || a->seg_state == nullptr || a->partials == nullptr || a->stamps == nullptr)
+        return fail(BNNP_E_ARG, "bnnp_finalize: null table pointer");
+    if ((a->pending.parity | 1) != 1) return fail(BNNP_E_ARG, "bnnp_finalize: parity must be 0 or 1");
+    bnnp_finalize_kernel<<<a->nseg, THREADS, 0, (cudaStream_t)stream>>>(*a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "bnnp_finalize_kernel launch");
+    return 0;
+}
+
+int bnnp_probe_stream(float* P, const float* G, float* M, int64_t total, void* stream) {
+    if (P == nullptr || G == nullptr || M == nullptr || total <= 0 || total % 4 != 0)
+        return fail(BNNP_E_ARG, "bnnp_probe_stream: bad argument");
+    const int64_t nquads = total / 4;
+    const int64_t blocks = (nquads + THREADS * UNROLL - 1) / (THREADS * UNROLL);
+    bnnp_probe_stream_kernel<<<(unsigned)blocks, THREADS, 0, (cudaStream_t)stream>>>(P, G, M, nquads);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "bnnp_probe_stream_kernel launch");
     return 0;
 }
 

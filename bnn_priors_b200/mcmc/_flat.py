@@ -162,8 +162,11 @@ class FlatGroup:
         self.state_host = torch.zeros(self.nseg, N.STATE_STRIDE, dtype=torch.float64).pin_memory()
         self.state_host[:, N.S_SQ_MEAN] = 1.0
         self.state_np = self.state_host.numpy()
-        self.partials = torch.empty(self.nchunks * N.NRED, dtype=torch.float64, device=dev)
-        self.tickets = torch.zeros(self.nseg, dtype=torch.int32, device=dev)
+        # per-chunk partial records of the last two launches (ping-pong) and their launch stamps
+        self.partials = torch.zeros(2 * self.nchunks * N.NRED, dtype=torch.float64, device=dev)
+        self.stamps = torch.zeros(2 * self.nchunks, dtype=torch.int64, device=dev)
+        self._parity = 0
+        self._pending = None     # epilogue parameters of the last launch, not yet applied to state_dev
         self._epoch = 0          # bumped by every launch / poke
         self._host_epoch = 0     # epoch state_host corresponds to
         self._mat_epoch = 0      # epoch the SegState dicts correspond to
@@ -288,12 +291,15 @@ class FlatGroup:
         self._lp_valid = False
 
     def _upload_table(self) -> None:
-        # rare (preconditioner / prior changes): a plain blocking copy of a few KB
+        # rare (preconditioner / prior changes): a plain blocking copy of a few KB.  The pending
+        # epilogue still needs the OLD table (it reads the preconditioner), so it runs first.
+        self.flush_pending()
         self.table_dev.copy_(torch.from_numpy(self.table.view(np.uint8).copy()))
         self._table_dirty = False
 
     # ------------------------------------------------------------ scalars
     def poke(self, i: int, col: int, v: float) -> None:
+        self.flush_pending()
         self.state_dev[i, col] = v
         self._epoch += 1
 
@@ -301,6 +307,7 @@ class FlatGroup:
         """Host mirror of the segment-state array (one D2H copy + one stream sync,
         only if a launch happened since the last fetch)."""
         if self._host_epoch != self._epoch:
+            self.flush_pending()
             self.state_host.copy_(self.state_dev, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             self._host_epoch = self._epoch
@@ -332,9 +339,60 @@ class FlatGroup:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _table_pointers(self, a) -> None:
+        a.segs, a.chunk_seg = self.table_dev.data_ptr(), self.chunk_seg_dev.data_ptr()
+        a.seg_state, a.partials, a.stamps = self.state_dev.data_ptr(), self.partials.data_ptr(), self.stamps.data_ptr()
+        a.nseg, a.nchunks_total = self.nseg, self.nchunks
+
+    def _set_pending(self, a) -> None:
+        e, pend = a.pending, self._pending
+        if pend is None:
+            e.valid = 0
+        else:
+            (e.valid, e.op, e.phase, e.flags, e.parity, e.call,
+             e.c_gm_base, e.curv_base, e.rms_alpha) = (1,) + pend
+
+    def _issue(self, a) -> None:
+        """bnnp_launch with this chain's deferred-epilogue protocol: the launch carries the
+        previous launch's epilogue (applied on the device by the first-chunk CTA of every
+        segment) and leaves its own pending."""
+        self._set_pending(a)
+        a.parity, a.call = self._parity, self.call
+        if torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                rc = self.lib.bnnp_launch(C.byref(a), self._stream())
+        else:
+            rc = self.lib.bnnp_launch(C.byref(a), self._stream())
+        N.check(rc, "bnnp_launch")
+        self._pending = (a.op, a.phase, a.flags, self._parity, self.call, a.c_gm_base, a.curv_base, a.rms_alpha)
+        self._parity ^= 1
+        self.call += 1
+        self._epoch += 1
+        self.launches += 1
+
+    def flush_pending(self) -> None:
+        """Apply the last launch's per-segment bookkeeping to state_dev now (bnnp_finalize).
+        Needed before the host reads state_dev, before the segment table changes and before a
+        launch that skips segments; a plain sequence of steps never calls it."""
+        if self._pending is None:
+            return
+        a = self.args
+        self._table_pointers(a)
+        self._set_pending(a)
+        if torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                rc = self.lib.bnnp_finalize(C.byref(a), self._stream())
+        else:
+            rc = self.lib.bnnp_finalize(C.byref(a), self._stream())
+        N.check(rc, "bnnp_finalize")
+        self._pending = None
+        self.launches += 1
+
     def launch(self, op: int, phase: int, flags: int, noise: int, cm=0.0, cg=0.0, cn=0.0, cp=0.0,
                inv_num_data=0.0, c_gm_base=0.0, curv_base=0.0, rms_alpha=0.0,
                chunks=None) -> None:
+        if chunks is not None:
+            self.flush_pending()      # every segment's pending epilogue needs a CTA; a partial launch has none for some
         if self._table_dirty:
             self._upload_table()
         a = self.args
@@ -350,37 +408,23 @@ class FlatGroup:
             a.replay_noise = self.replay.data_ptr()
         else:
             a.replay_noise = None
-        a.segs, a.chunk_seg = self.table_dev.data_ptr(), self.chunk_seg_dev.data_ptr()
+        self._table_pointers(a)
         a.chunk_ids = chunk_ids.data_ptr() if chunk_ids is not None else None
         self._chunk_ids_keepalive = chunk_ids
-        a.seg_state, a.partials, a.tickets = self.state_dev.data_ptr(), self.partials.data_ptr(), self.tickets.data_ptr()
-        a.nseg, a.nchunks = self.nseg, nchunks
+        a.nchunks = nchunks
         a.op, a.phase, a.noise, a.flags = op, phase, noise, flags
-        a.key0, a.key1, a.call = self.key[0], self.key[1], self.call
+        a.key0, a.key1 = self.key[0], self.key[1]
         a.cm, a.cg, a.cn, a.cp = cm, cg, cn, cp
         a.inv_num_data = inv_num_data
         a.grad_max = self.grad_max if self.grad_max is not None else 0.0
         a.c_gm_base, a.curv_base, a.rms_alpha = c_gm_base, curv_base, rms_alpha
-        if torch.cuda.current_device() != self.device.index:
-            with torch.cuda.device(self.device):
-                rc = self.lib.bnnp_launch(C.byref(a), self._stream())
-        else:
-            rc = self.lib.bnnp_launch(C.byref(a), self._stream())
-        N.check(rc, "bnnp_launch")
-        self.call += 1
-        self._epoch += 1
-        self.launches += 1
+        self._issue(a)
 
     def relaunch(self) -> None:
         """Launch again with the argument block of the previous launch (same
         coefficients, next Philox counter): the C-ABI-level hot loop that bench.py
         times for the device-resident number."""
-        a = self.args
-        a.call = self.call
-        N.check(self.lib.bnnp_launch(C.byref(a), self._stream()), "bnnp_launch")
-        self.call += 1
-        self._epoch += 1
-        self.launches += 1
+        self._issue(self.args)
 
     def chunks_without(self, missing: Sequence[int]):
         """(device list of chunk indices, count) that skips the segments in `missing`

@@ -124,6 +124,7 @@ class FusedPrior:
             if not fg.log_prior_fresh():
                 fg.sync_views(raise_on_no_grad=False)
                 fg.reduce_now(1.0 / self.sampler.param_groups[gi]['num_data'])
+            fg.flush_pending()          # the sum lives in the segment state once the last launch's epilogue ran
             v = fg.state_dev[:, N.S_LOG_PRIOR].sum()
             total = v if total is None else total + v
         lp = _EngineValue.apply(self._anchor, total.to(torch.float32))

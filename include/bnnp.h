@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BNNP_ABI_VERSION 4
+#define BNNP_ABI_VERSION 5
 
 #define BNNP_SEG_ALIGN 32      /* floats: every segment starts on a 128-byte line */
 #ifndef BNNP_THREADS
@@ -121,6 +121,20 @@ typedef struct BnnpSegment {
     int32_t num_chunks;  /* ceil(numel / BNNP_CHUNK)                           */
 } BnnpSegment;
 
+/* What the per-segment scalar bookkeeping (the "epilogue") of a launch needs.  It is
+ * not applied by the launch itself but by the NEXT bnnp_launch on the same chain
+ * (which receives it as BnnpLaunch.pending; its first nseg CTAs do the work) or by
+ * bnnp_finalize.  A launch with chunk_ids must not carry a pending epilogue. */
+typedef struct BnnpEpilogue {
+    int32_t valid;           /* 0: nothing pending                                  */
+    int32_t op, phase;
+    uint32_t flags;
+    int32_t parity;          /* which half of `partials` / `stamps` that launch wrote */
+    int32_t reserved;
+    uint64_t call;           /* its launch counter (stamps hold call + 1)           */
+    double c_gm_base, curv_base, rms_alpha;
+} BnnpEpilogue;
+
 typedef struct BnnpLaunch {
     float* P;                  /* flat [total]                                      */
     float* G;
@@ -135,9 +149,13 @@ typedef struct BnnpLaunch {
                                   chunk indices, whole segments only (used to skip
                                   tensors without a gradient, sgld.py:96-101)       */
     double* seg_state;         /* [nseg][BNNP_STATE_STRIDE]                         */
-    double* partials;          /* scratch [nchunks][BNNP_NRED]                      */
-    uint32_t* tickets;         /* [nseg], zero-initialised once                     */
-    int32_t nseg, nchunks;
+    double* partials;          /* scratch [2][nchunks_total][BNNP_NRED]             */
+    uint64_t* stamps;          /* [2][nchunks_total], zero-initialised once         */
+    int32_t nseg, nchunks;     /* nchunks: CTAs of this launch (= nchunks_total
+                                  unless chunk_ids is given)                        */
+    int32_t nchunks_total;     /* chunks of the whole chain (bnnp_plan_layout)      */
+    int32_t parity;            /* 0/1: half of partials/stamps this launch writes;
+                                  must differ from pending.parity                   */
     int32_t op, phase, noise;
     uint32_t flags;
     uint32_t key0, key1;       /* Philox key                                        */
@@ -149,6 +167,8 @@ typedef struct BnnpLaunch {
     double c_gm_base;          /* -bhn/2        (verlet_sgld.py:170)                */
     double curv_base;          /* N^2 b^2h^2/8  (verlet_sgld.py:46)                 */
     double rms_alpha;          /* sgld.py:153                                       */
+    BnnpEpilogue pending;      /* epilogue of the previous launch on this chain, to
+                                  be applied by this one (valid = 0: none)          */
 } BnnpLaunch;
 
 int bnnp_abi_version(void);
@@ -180,10 +200,23 @@ int bnnp_plan_layout(const int64_t* numel, int nseg,
  *                            models/base.py:72-77, inference.py:218-220        */
 int bnnp_launch(const BnnpLaunch* args, void* stream);
 
+/* Apply args->pending (the scalar bookkeeping of the last launch: state['delta_energy'],
+ * ['prev_new_momentum_delta'], est_* numerators, square_avg mean, log-prior --
+ * verlet_sgld.py:170-187, hmc.py:50-72, sgld.py:127-154) now, in a launch of nseg small
+ * CTAs.  Needed before the host reads seg_state, changes the segment table, or starts
+ * a launch that skips segments.  Reads segs, seg_state, partials, stamps, nseg,
+ * nchunks_total and pending; no-op if pending.valid == 0. */
+int bnnp_finalize(const BnnpLaunch* args, void* stream);
+
 /* VerletSGLD.maybe_reject's restore (mcmc/verlet_sgld.py:63-69):
  * P,G,M <- prev_*  over `total` floats (prev_m/M may be null: momentum == 0). */
 int bnnp_rollback(float* P, float* G, float* M, const float* prev_p, const float* prev_g,
                   const float* prev_m, int64_t total, void* stream);
+
+/* Diagnostic only (tools/tune_tiles.py): the bare memory access pattern of a step
+ * (read P, G, M; write P, M over `total` floats, two FMAs per element) -- the
+ * bandwidth ceiling the step kernel is compared against.  Overwrites P and M. */
+int bnnp_probe_stream(float* P, const float* G, float* M, int64_t total, void* stream);
 
 #ifdef __cplusplus
 }

@@ -100,10 +100,17 @@ def test_launch_validates_arguments_without_a_gpu(lib):
     assert lib.bnnp_launch(None, None) == -1
     a = N.BnnpLaunch()
     assert lib.bnnp_launch(C.byref(a), None) == -1 and b"empty chain" in lib.bnnp_last_error()
-    a.nseg, a.nchunks = 1, 1
+    a.nseg, a.nchunks, a.nchunks_total = 1, 1, 1
     assert lib.bnnp_launch(C.byref(a), None) == -1 and b"null table" in lib.bnnp_last_error()
-    for f in ("segs", "chunk_seg", "seg_state", "partials", "tickets"):   # chunk_ids may stay null
+    for f in ("segs", "chunk_seg", "seg_state", "partials", "stamps"):   # chunk_ids may stay null
         setattr(a, f, 4096)
+    a.nchunks = 2
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"does not match the plan" in lib.bnnp_last_error()
+    a.nchunks = 1
+    a.pending.valid, a.pending.parity, a.parity = 1, 0, 0
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"overwrite the partial records" in lib.bnnp_last_error()
+    a.pending.valid = 0
+    assert lib.bnnp_finalize(C.byref(a), None) == 0             # nothing pending: no-op, no CUDA call
     a.op = 9
     assert lib.bnnp_launch(C.byref(a), None) == -1 and b"bad op" in lib.bnnp_last_error()
     a.op, a.flags = N.OP_SGLD, N.F_READ_P

@@ -35,4 +35,16 @@ for name, smp, fused, call in cases:
     out[name] = [round(ms[0] * 1e3, 2), round(ms[2] * 1e3, 2)]      # min, median of 5
     del opt, params, fg
     torch.cuda.empty_cache()
+if not only or "probe" in only.split(","):
+    # ceiling of the access pattern: read p, g, m / write p, m and nothing else
+    from bnn_priors_b200 import _native as N
+    n = 25124864
+    P, G, M = (torch.zeros(n, device=dev) for _ in range(3))
+    lib = N.lib()
+    s = torch.cuda.current_stream(dev).cuda_stream
+    probe = lambda: N.check(lib.bnnp_probe_stream(P.data_ptr(), G.data_ptr(), M.data_ptr(), n, s), "probe")  # noqa: E731
+    for _ in range(200):
+        probe()
+    ms = sorted(bench.timed_gpu(probe, K, dev, False) / K for _ in range(5))
+    out["probe_stream"] = [round(ms[0] * 1e3, 2), round(ms[2] * 1e3, 2)]
 print(json.dumps(out), flush=True)
