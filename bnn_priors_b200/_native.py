@@ -24,6 +24,7 @@ NRED = 8
 STATE_STRIDE = 16
 
 PRIOR_NONE, PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T = 0, 1, 2, 3
+PRIOR_CAUCHY, PRIOR_GENNORM, PRIOR_LOGNORMAL, PRIOR_UNIFORM, PRIOR_IMPROPER, PRIOR_DOUBLE_GAMMA = 4, 5, 6, 7, 8, 9
 OP_SGLD, OP_VERLET, OP_HMC, OP_SAMPLE_MOMENTUM, OP_REDUCE = 0, 1, 2, 3, 4
 PHASE_INITIAL, PHASE_MID, PHASE_FINAL = 0, 1, 2
 NOISE_NONE, NOISE_REPLAY, NOISE_PHILOX = 0, 1, 2

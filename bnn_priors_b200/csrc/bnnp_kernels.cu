@@ -118,60 +118,120 @@ __device__ __forceinline__ void philox_normal4(uint64_t quad, uint64_t call, con
 // ---------------------------------------------------------------------------------
 // Priors.  Per-segment constants (uniform over the CTA).
 // ---------------------------------------------------------------------------------
+// The kernel evaluates five closed forms; the ten prior kinds of the ABI map onto them:
+//   F_NORMAL      Normal, LogNormal (= Normal in p plus the "- p" of prior/loc_scale.py:91)
+//   F_LAPLACE     Laplace
+//   F_STUDENT_T   StudentT, Cauchy (= StudentT with df = 1)
+//   F_GENNORM     GenNorm (prior/distributions.py:75-79)
+//   F_DOUBLE_GAMMA DoubleGamma (prior/transformed.py:83-96)
+//   F_NONE        no prior / Uniform / Improper: no gradient, a constant log density
+enum { F_NONE = 0, F_NORMAL, F_LAPLACE, F_STUDENT_T, F_GENNORM, F_DOUBLE_GAMMA };
+
 struct PriorConst {
-    int kind;
+    int form;       // F_*
     float loc;
-    float k;        // NORMAL: 1/(N s^2); LAPLACE: 1/(N s); STUDENT_T: 1/N
-    float a, b;     // STUDENT_T: a = df + 1, b = df s^2;  log-prob: see log_prior_term
+    float k;        // F_NORMAL: 1/(N s^2); F_LAPLACE: 1/(N s); others: 1/N
+    float c;        // F_NORMAL: the constant part of the gradient term (LogNormal: 1/N, else 0)
+    float lin;      // F_NORMAL: log density has "- lin * p" (LogNormal: 1, else 0)
+    float a, b;     // F_STUDENT_T: a = df + 1, b = df s^2;  F_GENNORM: a = beta;  F_DOUBLE_GAMMA: a = conc - 1
+    float la;       // F_STUDENT_T: -.5 (df + 1)
     float inv_s;    // 1/s
     float inv_df;
 };
 
 __device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double inv_n) {
     PriorConst pc;
-    pc.kind = sd.prior_kind;
+    const int kind = sd.prior_kind;
     pc.loc = sd.prior_loc;
-    const float s = sd.prior_scale, df = sd.prior_df;
+    const float s = sd.prior_scale;
+    const float df = (kind == BNNP_PRIOR_CAUCHY) ? 1.0f : sd.prior_df;
     pc.inv_s = 1.0f / s;
     pc.inv_df = 1.0f / df;
     pc.a = df + 1.0f;
     pc.b = df * s * s;
-    if (pc.kind == BNNP_PRIOR_NORMAL) pc.k = (float)(inv_n / ((double)s * (double)s));
-    else if (pc.kind == BNNP_PRIOR_LAPLACE) pc.k = (float)(inv_n / (double)s);
-    else pc.k = (float)inv_n;
+    pc.la = -0.5f * (df + 1.0f);
+    pc.c = 0.0f;
+    pc.lin = 0.0f;
+    pc.k = (float)inv_n;
+    switch (kind) {
+        case BNNP_PRIOR_LOGNORMAL:
+            pc.c = (float)inv_n;
+            pc.lin = 1.0f;
+            // fall through
+        case BNNP_PRIOR_NORMAL:
+            pc.form = F_NORMAL;
+            pc.k = (float)(inv_n / ((double)s * (double)s));
+            break;
+        case BNNP_PRIOR_LAPLACE:
+            pc.form = F_LAPLACE;
+            pc.k = (float)(inv_n / (double)s);
+            break;
+        case BNNP_PRIOR_STUDENT_T:
+        case BNNP_PRIOR_CAUCHY:
+            pc.form = F_STUDENT_T;
+            break;
+        case BNNP_PRIOR_GENNORM:
+            pc.form = F_GENNORM;
+            pc.a = sd.prior_df;            // beta
+            break;
+        case BNNP_PRIOR_DOUBLE_GAMMA:
+            pc.form = F_DOUBLE_GAMMA;
+            pc.a = sd.prior_df - 1.0f;     // concentration - 1
+            break;
+        default:
+            pc.form = F_NONE;
+    }
     return pc;
 }
 
 // -(1/N) d log p / d theta: what potential = loss - log_prior/N (models/base.py:76)
 // adds to p.grad through autograd in the reference.
-template <int KIND>
+template <int FORM>
 __device__ __forceinline__ float prior_grad_term(const PriorConst& pc, float p) {
     const float d = p - pc.loc;
-    if (KIND == BNNP_PRIOR_NORMAL) return d * pc.k;
-    if (KIND == BNNP_PRIOR_LAPLACE) return d == 0.0f ? 0.0f : copysignf(pc.k, d);
-    if (KIND == BNNP_PRIOR_STUDENT_T) return (pc.a * d) / fmaf(d, d, pc.b) * pc.k;
+    if (FORM == F_NORMAL) return fmaf(d, pc.k, pc.c);
+    if (FORM == F_LAPLACE) return d == 0.0f ? 0.0f : copysignf(pc.k, d);
+    if (FORM == F_STUDENT_T) return (pc.a * d) / fmaf(d, d, pc.b) * pc.k;
+    if (FORM == F_GENNORM) {            // beta |z|^(beta-1) sign(d) / (s N)
+        const float sg = d == 0.0f ? 0.0f : copysignf(1.0f, d);
+        return pc.a * powf(fabsf(d) * pc.inv_s, pc.a - 1.0f) * sg * pc.inv_s * pc.k;
+    }
+    if (FORM == F_DOUBLE_GAMMA) {       // (sign(d)/s - (c-1)/d) / N
+        const float sg = d == 0.0f ? 0.0f : copysignf(1.0f, d);
+        return (sg * pc.inv_s - pc.a / d) * pc.k;
+    }
     return 0.0f;
 }
 
 // the theta-dependent part of log p(theta); the per-element constant is added once
 // per segment in the epilogue (log_prior_const)
-template <int KIND>
+template <int FORM>
 __device__ __forceinline__ float log_prior_term(const PriorConst& pc, float p) {
-    const float z = (p - pc.loc) * pc.inv_s;
-    if (KIND == BNNP_PRIOR_NORMAL) return -0.5f * z * z;
-    if (KIND == BNNP_PRIOR_LAPLACE) return -fabsf(z);
-    if (KIND == BNNP_PRIOR_STUDENT_T) return -0.5f * pc.a * log1pf(z * z * pc.inv_df);
+    const float d = p - pc.loc;
+    const float z = d * pc.inv_s;
+    if (FORM == F_NORMAL) return fmaf(-pc.lin, p, -0.5f * z * z);
+    if (FORM == F_LAPLACE) return -fabsf(z);
+    if (FORM == F_STUDENT_T) return pc.la * log1pf(z * z * pc.inv_df);
+    if (FORM == F_GENNORM) return -powf(fabsf(z), pc.a);
+    if (FORM == F_DOUBLE_GAMMA) return pc.a * logf(fabsf(d)) - fabsf(z);
     return 0.0f;
 }
 
 __device__ double log_prior_const(const BnnpSegment& sd) {
     const double s = (double)sd.prior_scale, df = (double)sd.prior_df;
-    if (sd.prior_kind == BNNP_PRIOR_NORMAL) return -log(s) - 0.9189385332046727;  // .5 log 2pi
-    if (sd.prior_kind == BNNP_PRIOR_LAPLACE) return -log(2.0 * s);
-    if (sd.prior_kind == BNNP_PRIOR_STUDENT_T)
-        return -(log(s) + 0.5 * log(df) + 0.5723649429247001 /* .5 log pi */ + lgamma(0.5 * df) -
-                 lgamma(0.5 * (df + 1.0)));
-    return 0.0;
+    switch (sd.prior_kind) {
+        case BNNP_PRIOR_NORMAL:
+        case BNNP_PRIOR_LOGNORMAL: return -log(s) - 0.9189385332046727;   // .5 log 2pi
+        case BNNP_PRIOR_LAPLACE: return -log(2.0 * s);
+        case BNNP_PRIOR_STUDENT_T:
+            return -(log(s) + 0.5 * log(df) + 0.5723649429247001 /* .5 log pi */ + lgamma(0.5 * df) -
+                     lgamma(0.5 * (df + 1.0)));
+        case BNNP_PRIOR_CAUCHY: return -log(s) - 1.1447298858494002;      // log pi
+        case BNNP_PRIOR_GENNORM: return -log(2.0 * s) - lgamma(1.0 / df) + log(df);
+        case BNNP_PRIOR_UNIFORM: return -log(s);                          // s = high - low
+        case BNNP_PRIOR_DOUBLE_GAMMA: return -df * log(s) - lgamma(df) - 0.6931471805599453;
+        default: return 0.0;                                              // NONE, IMPROPER
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -218,7 +278,7 @@ __device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c,
         float gj = g.f[j];
         acc[R_NONFINITE] = fmaf(gj, 0.0f, acc[R_NONFINITE]);   // 0, or NaN once g is inf/NaN
         if (PRIOR) {
-            if (KIND != BNNP_PRIOR_NONE && (flags & BNNP_F_PRIOR_GRAD) && j < valid) gj += prior_grad_term<KIND>(pc, p0);
+            if (KIND != F_NONE && (flags & BNNP_F_PRIOR_GRAD) && j < valid) gj += prior_grad_term<KIND>(pc, p0);
             if (flags & BNNP_F_CLAMP_GRAD) gj = fminf(fmaxf(gj, -c.gmax), c.gmax);
         }
         float t, pre;
@@ -245,7 +305,7 @@ __device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c,
             acc[R_PG] = fmaf(p0, gj, acc[R_PG]);
         }
         const float pn = fmaf(c.cpM, t, p0);      // stored only with BNNP_F_WRITE_P
-        if (PRIOR && KIND != BNNP_PRIOR_NONE) {
+        if (PRIOR && KIND != F_NONE) {
             if ((flags & BNNP_F_LOG_PRIOR) && j < valid)
                 acc[R_LOGP] += log_prior_term<KIND>(pc, (flags & BNNP_F_WRITE_P) ? pn : p0);
         }
@@ -418,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS>()) bnnp_step_ke
     c.cpM = (float)(L.cp * sd.precond);
     c.gmax = (float)L.grad_max;
     PriorConst pc;
-    pc.kind = BNNP_PRIOR_NONE;
+    pc.form = F_NONE;
     if (PRIOR) pc = make_prior(sd, L.inv_num_data);
 
     PhiloxKeys keys;
@@ -443,21 +503,27 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS>()) bnnp_step_ke
     for (int k = 0; k < BNNP_NRED; ++k) acc[k] = 0.0f;
 
     if (PRIOR) {
-        switch (pc.kind) {
-            case BNNP_PRIOR_NORMAL:
-                process_chunk<NOISE, true, BNNP_PRIOR_NORMAL, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+        switch (pc.form) {   // uniform over the CTA: one closed form per segment
+            case F_NORMAL:
+                process_chunk<NOISE, true, F_NORMAL, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
                 break;
-            case BNNP_PRIOR_LAPLACE:
-                process_chunk<NOISE, true, BNNP_PRIOR_LAPLACE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+            case F_LAPLACE:
+                process_chunk<NOISE, true, F_LAPLACE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
                 break;
-            case BNNP_PRIOR_STUDENT_T:
-                process_chunk<NOISE, true, BNNP_PRIOR_STUDENT_T, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+            case F_STUDENT_T:
+                process_chunk<NOISE, true, F_STUDENT_T, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+                break;
+            case F_GENNORM:
+                process_chunk<NOISE, true, F_GENNORM, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+                break;
+            case F_DOUBLE_GAMMA:
+                process_chunk<NOISE, true, F_DOUBLE_GAMMA, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
                 break;
             default:
-                process_chunk<NOISE, true, BNNP_PRIOR_NONE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+                process_chunk<NOISE, true, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
         }
     } else {
-        process_chunk<NOISE, false, BNNP_PRIOR_NONE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+        process_chunk<NOISE, false, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
     }
 
     // ---- chunk reduction: fp32 butterfly inside the warp, fp64 across warps (fixed order)

@@ -18,8 +18,10 @@ closed form:
     grad_fn so that the runners' `.backward()` calls keep working
     (inference_reject.py:20-22).
 
-Priors that are not plain Normal / Laplace / StudentT with constant loc / scale / df
-(hierarchical, empirical-Bayes, mixtures, correlated, Improper, ...) are left alone:
+Covered: Normal, Laplace, StudentT (the north star's three) and, as the next row of the
+scope table, Cauchy, GenNorm, LogNormal, Uniform, Improper and DoubleGamma,
+all with constant hyper-parameters.  Everything else (hierarchical, empirical-Bayes,
+mixtures, correlated and multivariate priors, Gamma / HalfCauchy on softplus) is left alone:
 their log_prob stays in autograd and their gradient arrives in p.grad as before.
 `p.grad` of a fused tensor holds the LIKELIHOOD gradient only.
 """
@@ -27,12 +29,17 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import math
+
 import torch
 import torch.distributions as td
 
 from . import _native as N
 
-_KIND_OF_DIST = {td.Normal: N.PRIOR_NORMAL, td.Laplace: N.PRIOR_LAPLACE, td.StudentT: N.PRIOR_STUDENT_T}
+_KIND_OF_DIST = {td.Normal: N.PRIOR_NORMAL, td.Laplace: N.PRIOR_LAPLACE, td.StudentT: N.PRIOR_STUDENT_T,
+                 td.Cauchy: N.PRIOR_CAUCHY}
+# name of the third hyper-parameter (BnnpSegment.prior_df) per kind
+_THIRD = {N.PRIOR_STUDENT_T: "df", N.PRIOR_GENNORM: "beta", N.PRIOR_DOUBLE_GAMMA: "concentration"}
 
 
 def _is_prior_module(m: torch.nn.Module) -> bool:
@@ -40,31 +47,114 @@ def _is_prior_module(m: torch.nn.Module) -> bool:
         and hasattr(m, "kwargs_keys")
 
 
+def _constant(m, key):
+    "value of a one-element, non-trainable buffer `key` of `m`, else None"
+    v = m._buffers.get(key)
+    if not isinstance(v, torch.Tensor) or v.numel() != 1 or v.requires_grad:
+        return None
+    return float(v)
+
+
 def describe_prior(m: torch.nn.Module) -> Optional[tuple]:
-    """(kind, loc, scale, df) if `m` is a prior the kernel can evaluate exactly like
-    the reference does, else None.  Requirements: the class's `_dist` is
-    torch.distributions.{Normal, Laplace, StudentT}; `log_prob` is the base
-    `Prior.log_prob` (prior/base.py:57-58), not an override; loc / scale / df are
-    one-element buffers (constants), not Parameters or Prior modules."""
-    kind = _KIND_OF_DIST.get(getattr(type(m), "_dist", None))
+    """(kind, loc, scale, third) if `m` is a prior the kernel can evaluate exactly like
+    the reference does, else None.  Recognised (reference classes, prior/loc_scale.py and
+    prior/transformed.py): Normal, Laplace, StudentT, Cauchy, GenNorm -- classes that use
+    the base `Prior.log_prob` (prior/base.py:57-58) with the matching `_dist` -- and
+    LogNormal, Improper / PositiveImproper, Uniform, DoubleGamma, which override `log_prob`
+    and are recognised by the overriding class.  All hyper-parameters must be one-element
+    buffers (constants), not Parameters or Prior modules.  `fuse_prior` additionally checks
+    every recognised module numerically against its own `log_prob` + autograd."""
+    cls = type(m)
+    definer = next((k for k in cls.__mro__ if "log_prob" in k.__dict__), None)
+    if definer is None:
+        return None
+    dist = getattr(cls, "_dist", None)
+    keys = set(getattr(m, "kwargs_keys", ()))
+    name = definer.__name__
+    kind = None
+    if name == "Prior":
+        kind = _KIND_OF_DIST.get(dist)
+        if kind is None and getattr(dist, "__name__", "") == "GeneralizedNormal":
+            kind = N.PRIOR_GENNORM
+    elif name == "LogNormal" and dist is td.Normal:
+        kind = N.PRIOR_LOGNORMAL
+    elif name == "Improper":
+        return N.PRIOR_IMPROPER, 0.0, 1.0, 3.0
+    elif name == "Uniform" and dist is td.Uniform:
+        lo, hi = _constant(m, "low"), _constant(m, "high")
+        if keys != {"low", "high"} or lo is None or hi is None or not hi > lo:
+            return None
+        return N.PRIOR_UNIFORM, lo, hi - lo, 3.0
+    elif name == "DoubleGamma":
+        kind = N.PRIOR_DOUBLE_GAMMA
     if kind is None:
         return None
-    definer = next((k for k in type(m).__mro__ if "log_prob" in k.__dict__), None)
-    if definer is None or definer.__name__ != "Prior":
+    third = _THIRD.get(kind)
+    if keys != {"loc", "scale"} | ({third} if third else set()):
         return None
-    keys = set(getattr(m, "kwargs_keys", ()))
-    want = {"loc", "scale"} | ({"df"} if kind == N.PRIOR_STUDENT_T else set())
-    if keys != want:
+    loc, scale = _constant(m, "loc"), _constant(m, "scale")
+    t = _constant(m, third) if third else 3.0
+    if loc is None or scale is None or t is None or not scale > 0 or not t > 0:
         return None
-    vals = {}
-    for k in want:
-        v = m._buffers.get(k)
-        if not isinstance(v, torch.Tensor) or v.numel() != 1 or v.requires_grad:
-            return None
-        vals[k] = float(v)
-    if not vals["scale"] > 0:
-        return None
-    return kind, vals["loc"], vals["scale"], vals.get("df", 3.0)
+    return kind, loc, scale, t
+
+
+def closed_form(kind: int, p: torch.Tensor, loc: float, scale: float, third: float):
+    """(sum of log density, d log density / d p) in float64 -- the formulas the kernel
+    implements (csrc/bnnp_kernels.cu: prior_grad_term, log_prior_term, log_prior_const),
+    used to check a recognised module against its own log_prob before it is fused."""
+    p = p.detach().double()
+    d = p - loc
+    z = d / scale
+    n = p.numel()
+    if kind == N.PRIOR_NORMAL or kind == N.PRIOR_LOGNORMAL:
+        lp = (-0.5 * z * z).sum() - n * (math.log(scale) + 0.5 * math.log(2 * math.pi))
+        g = -d / scale ** 2
+        if kind == N.PRIOR_LOGNORMAL:
+            lp, g = lp - p.sum(), g - 1.0
+    elif kind == N.PRIOR_LAPLACE:
+        lp = -z.abs().sum() - n * math.log(2 * scale)
+        g = -torch.sign(d) / scale
+    elif kind in (N.PRIOR_STUDENT_T, N.PRIOR_CAUCHY):
+        df = 1.0 if kind == N.PRIOR_CAUCHY else third
+        lp = (-0.5 * (df + 1) * torch.log1p(z * z / df)).sum() - n * (
+            math.log(scale) + 0.5 * math.log(df) + 0.5 * math.log(math.pi)
+            + math.lgamma(0.5 * df) - math.lgamma(0.5 * (df + 1)))
+        g = -(df + 1) * d / (df * scale ** 2 + d * d)
+    elif kind == N.PRIOR_GENNORM:
+        lp = -(z.abs() ** third).sum() + n * (-math.log(2 * scale) - math.lgamma(1 / third) + math.log(third))
+        g = -third * z.abs() ** (third - 1) * torch.sign(d) / scale
+    elif kind == N.PRIOR_UNIFORM:
+        lp, g = torch.tensor(-n * math.log(scale), dtype=torch.float64, device=p.device), torch.zeros_like(p)
+    elif kind == N.PRIOR_IMPROPER:
+        lp, g = torch.zeros((), dtype=torch.float64, device=p.device), torch.zeros_like(p)
+    elif kind == N.PRIOR_DOUBLE_GAMMA:
+        lp = ((third - 1) * d.abs().log() - z.abs()).sum() + n * (
+            -third * math.log(scale) - math.lgamma(third) - math.log(2))
+        g = (third - 1) / d - torch.sign(d) / scale
+    else:
+        raise ValueError(kind)
+    return lp, g
+
+
+def matches_module(m: torch.nn.Module, spec: tuple, rtol: float = 1e-4) -> bool:
+    """Does the kernel's closed form reproduce `m.log_prob()` and its autograd gradient at
+    the current parameter value?  (Guards the class-name based recognition.)"""
+    with torch.enable_grad():
+        lp = m.log_prob()
+        if isinstance(lp, torch.Tensor) and lp.requires_grad:
+            (g,) = torch.autograd.grad(lp, m.p, allow_unused=True)
+        else:
+            g = None
+    g = torch.zeros_like(m.p) if g is None else g
+    want_lp, want_g = closed_form(spec[0], m.p, *spec[1:])
+    lp = float(lp.detach()) if isinstance(lp, torch.Tensor) else float(lp)
+    if not (math.isfinite(lp) and bool(torch.isfinite(g).all())):
+        return False
+    if abs(lp - float(want_lp)) > rtol * max(1.0, abs(lp)):
+        return False
+    scale = float(g.double().abs().mean()) + 1e-30
+    return bool(((g.double() - want_g).abs() <= rtol * (g.double().abs() + scale)).all())
 
 
 class _EngineValue(torch.autograd.Function):
@@ -83,7 +173,7 @@ class _EngineValue(torch.autograd.Function):
 class FusedPrior:
     """Handle returned by `fuse_prior`; `.unfuse()` restores the model."""
 
-    def __init__(self, model, sampler, grad_max: Optional[float]):
+    def __init__(self, model, sampler, grad_max: Optional[float], verify: bool = True):
         self.model, self.sampler = model, sampler
         self.fused_modules: List[torch.nn.Module] = []
         self.other_modules: List[torch.nn.Module] = []
@@ -98,6 +188,8 @@ class FusedPrior:
             if not _is_prior_module(m):
                 continue
             spec = describe_prior(m)
+            if spec is not None and verify and not matches_module(m, spec):
+                spec = None                   # same name, different density: leave it to autograd
             if spec is None or id(m.p) not in where:
                 self.other_modules.append(m)
                 continue
@@ -146,9 +238,9 @@ class FusedPrior:
             del self.model.__dict__["log_prior"]
 
 
-def fuse_prior(model: torch.nn.Module, sampler, grad_max: Optional[float] = None) -> FusedPrior:
+def fuse_prior(model: torch.nn.Module, sampler, grad_max: Optional[float] = None, verify: bool = True) -> FusedPrior:
     """Move the supported priors of `model` from autograd into `sampler`'s kernel.
     `grad_max` is the runner's gradient clamp (inference.py:219-220, default 1e6
     in experiments/train_bnn.py:84): the reference clamps likelihood + prior
     gradient together, so the kernel re-applies it to the fused sum."""
-    return FusedPrior(model, sampler, grad_max)
+    return FusedPrior(model, sampler, grad_max, verify)

@@ -46,9 +46,22 @@ extern "C" {
 
 enum { BNNP_E_ARG = -1, BNNP_E_ALIGN = -2, BNNP_E_UNSUPPORTED = -3 };
 
-/* prior kinds (reference: prior/loc_scale.py:34-35 Normal, :66-67 Laplace,
- * :74-77 StudentT; NONE = the prior gradient is already inside G) */
-enum { BNNP_PRIOR_NONE = 0, BNNP_PRIOR_NORMAL = 1, BNNP_PRIOR_LAPLACE = 2, BNNP_PRIOR_STUDENT_T = 3 };
+/* prior kinds: elementwise priors with constant hyper-parameters.  NONE = the prior
+ * gradient is already inside G.  (prior_loc, prior_scale, prior_df) hold:
+ *   NORMAL       loc, scale, -          prior/loc_scale.py:34-35
+ *   LAPLACE      loc, scale, -          prior/loc_scale.py:66-67
+ *   STUDENT_T    loc, scale, df         prior/loc_scale.py:74-77
+ *   CAUCHY       loc, scale, -          prior/loc_scale.py:70-71
+ *   GENNORM      loc, scale, beta       prior/loc_scale.py:80-83, distributions.py:75-79
+ *   LOGNORMAL    loc, scale, -          prior/loc_scale.py:86-92 (density of p, incl. "- p")
+ *   UNIFORM      low, high - low, -     prior/transformed.py:12-47 (constant density of p)
+ *   IMPROPER     -, -, -                prior/loc_scale.py:94-97 (log_prob == 0)
+ *   DOUBLE_GAMMA loc, scale, concentration   prior/transformed.py:83-96 */
+enum {
+    BNNP_PRIOR_NONE = 0, BNNP_PRIOR_NORMAL = 1, BNNP_PRIOR_LAPLACE = 2, BNNP_PRIOR_STUDENT_T = 3,
+    BNNP_PRIOR_CAUCHY = 4, BNNP_PRIOR_GENNORM = 5, BNNP_PRIOR_LOGNORMAL = 6, BNNP_PRIOR_UNIFORM = 7,
+    BNNP_PRIOR_IMPROPER = 8, BNNP_PRIOR_DOUBLE_GAMMA = 9
+};
 
 /* which sampler's bookkeeping the per-segment epilogue applies */
 enum {

@@ -38,6 +38,8 @@ import numpy as np
 F32 = np.float32
 
 PRIOR_NONE, PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T = 0, 1, 2, 3
+# the other elementwise priors with constant hyper-parameters
+PRIOR_CAUCHY, PRIOR_GENNORM, PRIOR_LOGNORMAL, PRIOR_UNIFORM, PRIOR_IMPROPER, PRIOR_DOUBLE_GAMMA = 4, 5, 6, 7, 8, 9
 PHASE_INITIAL, PHASE_MID, PHASE_FINAL = 0, 1, 2
 
 
@@ -129,8 +131,10 @@ def philox_normal_segment(key, call: int, flat_offset: int, numel: int):
 # summed per tensor in prior/base.py:57-58).
 # --------------------------------------------------------------------------
 def prior_log_prob(kind: int, p, loc: float, scale: float, df: float = 3.0) -> float:
-    """Sum over the tensor of log density, accumulated in fp64 of fp32 terms."""
-    if kind == PRIOR_NONE:
+    """Sum over the tensor of log density, accumulated in fp64 of fp32 terms.
+    `df` is the third hyper-parameter of the kind: StudentT df, GenNorm beta,
+    DoubleGamma concentration.  For UNIFORM, loc = low and scale = high - low."""
+    if kind in (PRIOR_NONE, PRIOR_IMPROPER):        # Improper.log_prob == 0.0 (prior/loc_scale.py:94-97)
         return 0.0
     p = np.asarray(p, dtype=F32)
     loc, scale, df = F32(loc), F32(scale), F32(df)
@@ -144,6 +148,23 @@ def prior_log_prob(kind: int, p, loc: float, scale: float, df: float = 3.0) -> f
         norm = (np.log(scale) + F32(0.5) * np.log(df) + F32(0.5 * math.log(math.pi))
                 + F32(math.lgamma(0.5 * float(df)) - math.lgamma(0.5 * (float(df) + 1.0))))
         lp = F32(-0.5) * (df + F32(1.0)) * np.log1p(z * z / df) - norm
+    elif kind == PRIOR_CAUCHY:                      # td.Cauchy.log_prob (prior/loc_scale.py:70-71)
+        z = (p - loc) / scale
+        lp = -F32(math.log(math.pi)) - np.log(scale) - np.log1p(z * z)
+    elif kind == PRIOR_GENNORM:                     # prior/distributions.py:75-79, beta = df
+        lp = (-np.log(F32(2.0) * scale) - F32(math.lgamma(1.0 / float(df))) + np.log(df)
+              - np.power(np.abs(p - loc) / scale, df))
+    elif kind == PRIOR_LOGNORMAL:                   # Normal.log_prob(p) - p  (prior/loc_scale.py:86-92)
+        z = (p - loc) / scale
+        lp = F32(-0.5) * z * z - np.log(scale) - F32(0.5 * math.log(2 * math.pi)) - p
+    elif kind == PRIOR_UNIFORM:                     # -log(high - low) per element (prior/transformed.py:32-45)
+        lp = np.full(p.shape, -np.log(scale), dtype=F32)
+    elif kind == PRIOR_DOUBLE_GAMMA:                # Gamma(c, 1/s).log_prob(|p - loc|) - log 2
+        a = np.abs(p - loc)                         # (prior/transformed.py:83-96, distributions.py:97-110)
+        c = df
+        rate = F32(1.0) / scale
+        lp = (c * np.log(rate) + (c - F32(1.0)) * np.log(a) - rate * a
+              - F32(math.lgamma(float(c))) - F32(math.log(2.0)))
     else:
         raise ValueError(kind)
     return float(np.sum(lp.astype(np.float64)))
@@ -152,7 +173,7 @@ def prior_log_prob(kind: int, p, loc: float, scale: float, df: float = 3.0) -> f
 def prior_grad_log_prob(kind: int, p, loc: float, scale: float, df: float = 3.0):
     """d log density / d p, fp32 (what autograd returns for Prior.log_prob)."""
     p = np.asarray(p, dtype=F32)
-    if kind == PRIOR_NONE:
+    if kind in (PRIOR_NONE, PRIOR_UNIFORM, PRIOR_IMPROPER):
         return np.zeros_like(p)
     loc, scale, df = F32(loc), F32(scale), F32(df)
     d = p - loc
@@ -162,6 +183,14 @@ def prior_grad_log_prob(kind: int, p, loc: float, scale: float, df: float = 3.0)
         return -np.sign(d) / scale
     if kind == PRIOR_STUDENT_T:
         return -(df + F32(1.0)) * d / (df * scale * scale + d * d)
+    if kind == PRIOR_CAUCHY:
+        return F32(-2.0) * d / (scale * scale + d * d)
+    if kind == PRIOR_GENNORM:
+        return -df * np.power(np.abs(d) / scale, df - F32(1.0)) * np.sign(d) / scale
+    if kind == PRIOR_LOGNORMAL:
+        return -d / (scale * scale) - F32(1.0)
+    if kind == PRIOR_DOUBLE_GAMMA:
+        return (df - F32(1.0)) / d - np.sign(d) / scale
     raise ValueError(kind)
 
 

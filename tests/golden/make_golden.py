@@ -397,20 +397,49 @@ def golden_priors():
              ("laplace", ref_prior.Laplace, dict(loc=0.0, scale=0.3)),
              ("laplace_shift", ref_prior.Laplace, dict(loc=-0.5, scale=1.7)),
              ("studentt", ref_prior.StudentT, dict(loc=0.0, scale=0.2, df=3.0)),
-             ("studentt_df7", ref_prior.StudentT, dict(loc=0.25, scale=1.5, df=7.0))]
+             ("studentt_df7", ref_prior.StudentT, dict(loc=0.25, scale=1.5, df=7.0)),
+             # the other elementwise priors with constant hyper-parameters
+             ("cauchy", ref_prior.Cauchy, dict(loc=0.0, scale=0.05)),
+             ("cauchy_shift", ref_prior.Cauchy, dict(loc=-1.0, scale=2.5)),
+             ("gennorm", ref_prior.GenNorm, dict(loc=0.0, scale=0.4, beta=0.5)),
+             ("gennorm_b15", ref_prior.GenNorm, dict(loc=0.5, scale=1.2, beta=1.5)),
+             ("lognormal", ref_prior.LogNormal, dict(loc=-1.0, scale=0.2)),
+             ("uniform", ref_prior.Uniform, dict(low=-2.0, high=3.0)),
+             ("improper", ref_prior.Improper, dict(loc=0.0, scale=1.0)),
+             ("doublegamma", ref_prior.DoubleGamma, dict(loc=0.0, scale=0.3, concentration=1.7)),
+             ("doublegamma_c05", ref_prior.DoubleGamma, dict(loc=0.2, scale=2.0, concentration=0.5))]
+    KIND = {"Normal": 1, "Laplace": 2, "StudentT": 3, "Cauchy": 4, "GenNorm": 5, "LogNormal": 6, "Uniform": 7,
+            "Improper": 8, "DoubleGamma": 9}
     meta = []
     for name, cls, kw in cases:
         pm = cls(torch.Size([513]), **kw)
+        loc = kw.get("loc", 0.0)
+        scale = kw.get("scale", 1.0)
+        smooth_at_loc = cls.__name__ in ("Normal", "Laplace", "StudentT", "Cauchy", "LogNormal", "Uniform", "Improper")
         with torch.no_grad():
-            pm.p.copy_(torch.randn(513) * 3 * kw["scale"] + kw["loc"])
-            pm.p[0] = kw["loc"]                    # the kink of the Laplace density
-            pm.p[1] = kw["loc"] + 50 * kw["scale"]  # far tail
+            pm.p.copy_(torch.randn(513) * 3 * scale + loc)
+            if smooth_at_loc:
+                pm.p[0] = loc                       # the kink of the Laplace density
+            pm.p[1] = loc + 50 * scale              # far tail
         lp = pm.log_prob()
-        (g,) = torch.autograd.grad(lp, pm.p)
+        if isinstance(lp, float) or not lp.requires_grad:   # Improper: the float 0.0; Uniform: a constant
+            lp_val, g = float(lp), torch.zeros(513)
+        else:
+            lp_val = float(lp)
+            (g,) = torch.autograd.grad(lp, pm.p, allow_unused=True)
+            g = torch.zeros(513) if g is None else g
         out[name + "_p"] = pm.p.detach().numpy().copy()
         out[name + "_grad"] = g.numpy().copy()
-        meta.append(dict(name=name, kind={"Normal": 1, "Laplace": 2, "StudentT": 3}[cls.__name__],
-                         log_prob=float(lp), **kw))
+        row = dict(name=name, kind=KIND[cls.__name__], log_prob=lp_val, loc=loc, scale=scale)
+        if "df" in kw:
+            row["df"] = kw["df"]
+        if "beta" in kw:
+            row["df"] = kw["beta"]                  # third hyper-parameter slot
+        if "concentration" in kw:
+            row["df"] = kw["concentration"]
+        if cls.__name__ == "Uniform":
+            row.update(loc=kw["low"], scale=kw["high"] - kw["low"])
+        meta.append(row)
     np.savez_compressed(os.path.join(HERE, "priors.npz"),
                         meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **out)
     print("priors:", [m["name"] for m in meta])

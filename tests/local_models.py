@@ -57,6 +57,82 @@ class StudentT(Prior):
         super().__init__(shape, df=df, loc=loc, scale=scale)
 
 
+class Cauchy(Prior):
+    _dist = td.Cauchy
+
+    def __init__(self, shape, loc=0., scale=1.):
+        super().__init__(shape, loc=loc, scale=scale)
+
+
+class GeneralizedNormal(td.Distribution):
+    "density of prior/distributions.py:14-79 (log_prob only; sampling through a Laplace proxy)"
+    arg_constraints = {}
+
+    def __init__(self, loc, scale, beta):
+        self.loc, self.scale, self.beta = loc, scale, beta
+        super().__init__(validate_args=False)
+
+    def sample(self, sample_shape=torch.Size()):
+        return td.Laplace(self.loc, self.scale).sample(sample_shape)
+
+    def log_prob(self, value):
+        return (-torch.log(2 * self.scale) - torch.lgamma(1 / self.beta) + torch.log(self.beta)
+                - torch.pow(torch.abs(value - self.loc) / self.scale, self.beta))
+
+
+class GenNorm(Prior):
+    _dist = GeneralizedNormal
+
+    def __init__(self, shape, loc=0., scale=1., beta=0.5):
+        super().__init__(shape, loc=loc, scale=scale, beta=beta)
+
+
+class LogNormal(Prior):
+    "prior/loc_scale.py:86-92: the parameter lives in log space, the layer sees exp(p)"
+    _dist = td.Normal
+
+    def __init__(self, shape, loc=0., scale=1.):
+        super().__init__(shape, loc=loc, scale=scale)
+
+    def forward(self):
+        return self.p.exp()
+
+    def log_prob(self):
+        return super().log_prob() - self.p.sum()
+
+
+class Uniform(Prior):
+    "prior/transformed.py:12-47: a Gaussian variable pushed through its CDF; constant density of p"
+    _dist = td.Uniform
+
+    def __init__(self, shape, low, high):
+        super().__init__(shape, low=low, high=high)
+        with torch.no_grad():
+            self.p.copy_(torch.randn(shape))
+
+    def forward(self):
+        return self.low + (self.high - self.low) * td.Normal(0., 1.).cdf(self.p)
+
+    def log_prob(self):
+        return -torch.log(self.high - self.low) * self.p.numel()
+
+
+class DoubleGamma(Prior):
+    "prior/transformed.py:83-96"
+
+    def __init__(self, shape, loc=0., scale=1., concentration=1.5):
+        super().__init__(shape, loc=loc, scale=scale, concentration=concentration)
+
+    def _dist(self, loc, scale, concentration):
+        return td.Gamma(concentration, 1 / scale)
+
+    def _dist_obj(self):
+        return self._dist(self.loc, self.scale, self.concentration)
+
+    def log_prob(self):
+        return (self._dist_obj().log_prob((self.p - self.loc).abs()) - math.log(2)).sum()
+
+
 class Improper(Normal):
     "a prior the kernel must NOT fuse: log_prob is overridden (prior/loc_scale.py:94-97)"
 

@@ -62,13 +62,26 @@ def test_runner_trace_has_the_call_order_of_the_reference_runner():
 def test_priors_against_reference_log_prob_and_autograd():
     z = np.load(os.path.join(GOLDEN_DIR, "priors.npz"))
     meta = json.loads(bytes(z["meta"]).decode())
-    assert {m["kind"] for m in meta} == {1, 2, 3}
+    assert {m["kind"] for m in meta} == {1, 2, 3, 4, 5, 6, 7, 8, 9}
     for m in meta:
         p, g = z[m["name"] + "_p"], z[m["name"] + "_grad"]
         lp = O.prior_log_prob(m["kind"], p, m["loc"], m["scale"], m.get("df", 3.0))
         assert math.isclose(lp, m["log_prob"], rel_tol=2e-6), (m["name"], lp, m["log_prob"])
         got = O.prior_grad_log_prob(m["kind"], p, m["loc"], m["scale"], m.get("df", 3.0))
         np.testing.assert_allclose(got, g, rtol=3e-6, atol=1e-30, err_msg=m["name"])
+
+
+def test_host_closed_forms_match_reference_log_prob_and_autograd():
+    """bnn_priors_b200.prior_fusion.closed_form (the check fuse_prior runs before it fuses a
+    module) against the same golden vectors."""
+    import torch
+    from bnn_priors_b200.prior_fusion import closed_form
+    z = np.load(os.path.join(GOLDEN_DIR, "priors.npz"))
+    for m in json.loads(bytes(z["meta"]).decode()):
+        p, g = torch.tensor(z[m["name"] + "_p"]), z[m["name"] + "_grad"]
+        lp, grad = closed_form(m["kind"], p, m["loc"], m["scale"], m.get("df", 3.0))
+        assert math.isclose(float(lp), m["log_prob"], rel_tol=5e-6, abs_tol=1e-6), m["name"]
+        np.testing.assert_allclose(grad.numpy(), g, rtol=1e-5, atol=1e-7 * max(1.0, float(np.abs(g).max())), err_msg=m["name"])
 
 
 def test_philox_known_answers():
