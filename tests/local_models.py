@@ -134,7 +134,7 @@ class DoubleGamma(Prior):
 
 
 class Improper(Normal):
-    "a prior the kernel must NOT fuse: log_prob is overridden (prior/loc_scale.py:94-97)"
+    "log_prob is overridden to zero (prior/loc_scale.py:94-97): fused as a prior without gradient"
 
     def log_prob(self):
         return 0. * self.p.sum()

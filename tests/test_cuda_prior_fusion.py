@@ -116,7 +116,7 @@ def test_log_prior_is_recomputed_when_parameters_change():
 
 def test_unsupported_priors_stay_in_autograd():
     from bnn_priors_b200.prior_fusion import describe_prior, fuse_prior
-    assert describe_prior(LM.Improper((3,), 0., 1.)) is None
+    assert describe_prior(LM.Improper((3,), 0., 1.)) == (8, 0.0, 1.0, 3.0)      # log_prob == 0: no gradient, no value
     assert describe_prior(LM.LearnedScaleNormal((3,), 0., 1.)) is None
     assert describe_prior(LM.Normal((3,), 0.5, 2.0)) == (1, 0.5, 2.0, 3.0)
     assert describe_prior(LM.StudentT((3,), 0., 2.0, 5.0)) == (3, 0.0, 2.0, 5.0)
