@@ -151,3 +151,71 @@ def test_grad_clamp_is_applied_to_the_fused_sum():
         oa.step(); ob.step()
     for pa, pb in zip(ma.parameters(), mb.parameters()):
         assert torch.allclose(pa, pb, rtol=2e-5, atol=2e-6)
+
+
+def test_reject_runner_cycle_with_exact_gradients():
+    """the call sequence of VerletSGLDRunnerReject (inference_reject.py:18-33,
+    57-59, 88-91, 119-127, 156) -- full-data gradients ACCUMULATED over minibatches into the
+    flat G array, prior term backpropagated once -- with the prior in autograd (A) and fused
+    (B): same potentials, same delta_energy, same accept/reject decisions, same parameters."""
+    from bnn_priors_b200.prior_fusion import fuse_prior
+    n = 96.0
+    ma, oa, x, y = _setup(LM.StudentT, dict(df=3.0), extra_bn=True)
+    mb, ob, _, _ = _setup(LM.StudentT, dict(df=3.0), extra_bn=True)
+    mb.load_state_dict(ma.state_dict())
+    fuse_prior(mb, ob, grad_max=1e6)
+    batches = [(x[i:i + 32], y[i:i + 32]) for i in range(0, 96, 32)]
+
+    def exact(model, opt):                      # inference_reject.py:18-33
+        opt.zero_grad()
+        log_prior = model.log_prior()
+        log_norm_prior = log_prior / -n
+        log_norm_prior.backward()
+        loss = 0.
+        for xb, yb in batches:
+            this_loss = -torch.distributions.Categorical(logits=model.net(xb)).log_prob(yb).sum() / n
+            this_loss.backward()                # accumulates into p.grad = views of the flat G
+            loss = loss + this_loss
+        return float(loss + log_norm_prior)
+
+    ga, gb = torch.Generator().manual_seed(2), torch.Generator().manual_seed(2)
+    ua, ub = exact(ma, oa), exact(mb, ob)
+    assert ua == pytest.approx(ub, rel=2e-6)
+    _noise(oa, ga); _noise(ob, gb)
+    oa.sample_momentum(); ob.sample_momentum()
+    _noise(oa, ga); _noise(ob, gb)
+    oa.initial_step(calc_metrics=True, save_state=True); ob.initial_step(calc_metrics=True, save_state=True)
+    decisions = []
+    for epoch in range(4):
+        for xb, yb in batches:                  # the minibatch steps of an epoch (:88-91)
+            _runner_step(ma, oa, xb, yb, n); _runner_step(mb, ob, xb, yb, n)
+            _noise(oa, ga); _noise(ob, gb)
+            oa.step(calc_metrics=False); ob.step(calc_metrics=False)
+        va, vb = exact(ma, oa), exact(mb, ob)   # (:119)
+        assert va == pytest.approx(vb, rel=5e-6)
+        _noise(oa, ga); _noise(ob, gb)
+        oa.final_step(calc_metrics=True); ob.final_step(calc_metrics=True)
+        da, db = oa.delta_energy(ua, va), ob.delta_energy(ub, vb)
+        assert da == pytest.approx(db, rel=1e-4, abs=2e-3), (epoch, da, db)
+        u = [0.9, 1e-4, 0.5, 0.2][epoch]
+        real = torch.rand
+        torch.rand = lambda *a, **k: torch.tensor(u)
+        try:
+            ra, rb = oa.maybe_reject(da), ob.maybe_reject(db)
+        finally:
+            torch.rand = real
+        assert ra[0] == rb[0]
+        decisions.append(ra[0])
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            assert torch.allclose(pa, pb, rtol=5e-5, atol=5e-6), epoch
+        # store_metrics (inference.py:262-279): every per-tensor scalar comes from one device read
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            for k in ("preconditioner", "est_temperature", "est_config_temp"):
+                assert oa.state[pa][k] == pytest.approx(ob.state[pb][k], rel=1e-4, abs=1e-5), (epoch, k)
+        if ra[0]:                               # a rejected proposal restores the old potential (:127-139)
+            ua, ub = exact(ma, oa), exact(mb, ob)
+        else:
+            ua, ub = va, vb
+        _noise(oa, ga); _noise(ob, gb)
+        oa.initial_step(calc_metrics=False, save_state=True); ob.initial_step(calc_metrics=False, save_state=True)
+    assert len(decisions) == 4
