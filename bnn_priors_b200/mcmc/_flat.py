@@ -99,6 +99,16 @@ class SegState(dict):
             return
         dict.__setitem__(self, k, v)
 
+    def __delitem__(self, k):
+        if k == "momentum_buffer":
+            self._fg._mom_published = False
+        dict.__delitem__(self, k)
+
+    def pop(self, k, *default):
+        if k == "momentum_buffer":
+            self._fg._mom_published = False
+        return dict.pop(self, k, *default)
+
     def raw_get(self, k, default=None):
         return dict.get(self, k, default)
 
@@ -126,6 +136,7 @@ class FlatGroup:
             if p.numel() == 0:
                 raise RuntimeError("zero-sized parameters are not supported")
         self.device = dev
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         self.lib = N.lib()
         self.numel = [int(p.numel()) for p in self.params]
         self.nseg = len(self.params)
@@ -151,6 +162,7 @@ class FlatGroup:
         self.G = torch.zeros(total, dtype=torch.float32, device=dev)
         self.M: Optional[torch.Tensor] = None
         self.prev_p = self.prev_g = self.prev_m = None
+        self._ptrs = {"P": self.P.data_ptr(), "G": self.G.data_ptr()}     # device addresses of the flat arrays
         self.p_views = [self.P[o:o + n].view(p.shape) for o, n, p in zip(self.off, self.numel, self.params)]
         self.g_views = [self.G[o:o + n].view(p.shape) for o, n, p in zip(self.off, self.numel, self.params)]
         self.m_views: Optional[List[torch.Tensor]] = None
@@ -187,7 +199,10 @@ class FlatGroup:
         self._gg_version = None
         self._mm_version = None
 
+        self._mom_published = False
+        self._tables_set = False
         self.seg_states = [SegState(self, i) for i in range(self.nseg)]
+        self._sync_rows = list(zip(self.params, self.g_views, self.p_views, self._p_ptrs))
         self.args = N.BnnpLaunch()
         self.launches = 0
 
@@ -212,25 +227,28 @@ class FlatGroup:
         `p.grad = None`, `Prior.sample()`).  Returns the indices of parameters that
         have no gradient (sgld.py:96-101)."""
         missing: List[int] = []
-        gv, pv, ptrs = self.g_views, self.p_views, self._p_ptrs
-        for i, p in enumerate(self.params):
+        i = 0
+        for p, gv, pv, ptr in self._sync_rows:
             g = p.grad
-            if g is None:
-                if raise_on_no_grad:
-                    raise RuntimeError(f"No gradient for parameter with shape {p.shape}")
-                missing.append(i)
-            elif g is not gv[i]:
-                gv[i].copy_(g)
-                p.grad = gv[i]
-            if p.data_ptr() != ptrs[i]:
-                pv[i].copy_(p.data)
-                p.data = pv[i]
+            if g is not gv:
+                if g is None:
+                    if raise_on_no_grad:
+                        raise RuntimeError(f"No gradient for parameter with shape {p.shape}")
+                    missing.append(i)
+                else:
+                    gv.copy_(g)
+                    p.grad = gv
+            if p.data_ptr() != ptr:
+                pv.copy_(p.data)
+                p.data = pv
                 self._lp_valid = False
+            i += 1
         return missing
 
     def ensure_momentum_storage(self) -> None:
         if self.M is None:
             self.M = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+            self._ptrs["M"] = self.M.data_ptr()
             self.m_views = [self.M[o:o + n].view(p.shape) for o, n, p in zip(self.off, self.numel, self.params)]
 
     def set_momentum(self, i: int, value: torch.Tensor) -> torch.Tensor:
@@ -245,24 +263,30 @@ class FlatGroup:
 
     def check_momentum(self) -> None:
         """sgld.py:107-111: stepping without sample_momentum is an error."""
+        if self._mom_published:
+            return
         if self.M is None or any(s.raw_get("momentum_buffer") is None for s in self.seg_states):
             raise RuntimeError("No 'momentum_buffer' stored in state. "
                                "Perhaps you forgot to call `sample_momentum`?")
+        self._mom_published = True
 
     def publish_momentum(self) -> None:
         for s, v in zip(self.seg_states, self.m_views):
             if s.raw_get("momentum_buffer") is not v:
                 s.raw_set("momentum_buffer", v)
+        self._mom_published = True
 
     def ensure_prev_storage(self, with_momentum: bool) -> None:
         if self.prev_p is None:
             self.prev_p = torch.zeros_like(self.P)
             self.prev_g = torch.zeros_like(self.P)
+            self._ptrs["prev_p"], self._ptrs["prev_g"] = self.prev_p.data_ptr(), self.prev_g.data_ptr()
             for s, o, n, p in zip(self.seg_states, self.off, self.numel, self.params):
                 s.raw_set("prev_parameter", self.prev_p[o:o + n].view(p.shape))
                 s.raw_set("prev_grad", self.prev_g[o:o + n].view(p.shape))
         if with_momentum and self.prev_m is None:
             self.prev_m = torch.zeros_like(self.P)
+            self._ptrs["prev_m"] = self.prev_m.data_ptr()
             for s, o, n, p in zip(self.seg_states, self.off, self.numel, self.params):
                 s.raw_set("prev_momentum_buffer", self.prev_m[o:o + n].view(p.shape))
 
@@ -337,12 +361,15 @@ class FlatGroup:
 
     # ------------------------------------------------------------ launches
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
     def _table_pointers(self, a) -> None:
+        if self._tables_set:
+            return
         a.segs, a.chunk_seg = self.table_dev.data_ptr(), self.chunk_seg_dev.data_ptr()
         a.seg_state, a.partials, a.stamps = self.state_dev.data_ptr(), self.partials.data_ptr(), self.stamps.data_ptr()
         a.nseg, a.nchunks_total = self.nseg, self.nchunks
+        self._tables_set = True
 
     def _set_pending(self, a) -> None:
         e, pend = a.pending, self._pending
@@ -358,7 +385,7 @@ class FlatGroup:
         segment) and leaves its own pending."""
         self._set_pending(a)
         a.parity, a.call = self._parity, self.call
-        if torch.cuda.current_device() != self.device.index:
+        if torch.cuda.current_device() != self._dev_index:
             with torch.cuda.device(self.device):
                 rc = self.lib.bnnp_launch(C.byref(a), self._stream())
         else:
@@ -379,7 +406,7 @@ class FlatGroup:
         a = self.args
         self._table_pointers(a)
         self._set_pending(a)
-        if torch.cuda.current_device() != self.device.index:
+        if torch.cuda.current_device() != self._dev_index:
             with torch.cuda.device(self.device):
                 rc = self.lib.bnnp_finalize(C.byref(a), self._stream())
         else:
@@ -397,11 +424,10 @@ class FlatGroup:
             self._upload_table()
         a = self.args
         chunk_ids, nchunks = chunks if chunks is not None else (None, self.nchunks)
-        a.P, a.G = self.P.data_ptr(), self.G.data_ptr()
-        a.M = self.M.data_ptr() if self.M is not None else None
-        a.prev_p = self.prev_p.data_ptr() if self.prev_p is not None else None
-        a.prev_g = self.prev_g.data_ptr() if self.prev_g is not None else None
-        a.prev_m = self.prev_m.data_ptr() if (self.prev_m is not None and (flags & N.F_READ_M)) else None
+        ptr = self._ptrs
+        a.P, a.G, a.M = ptr["P"], ptr["G"], ptr.get("M")
+        a.prev_p, a.prev_g = ptr.get("prev_p"), ptr.get("prev_g")
+        a.prev_m = ptr.get("prev_m") if (flags & N.F_READ_M) else None
         if noise == N.NOISE_REPLAY:
             if self.replay is None:
                 raise RuntimeError("replay noise requested but none was provided")
