@@ -60,13 +60,23 @@ enum { R_GM_OLD = 0, R_GM_NEW, R_MM_OLD, R_MM_NEW, R_PG, R_GG, R_LOGP, R_NONFINI
 // ---------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11) and the Box-Muller transform specified in
 // oracle/sgmcmc_oracle.py:_box_muller.  The round keys are uniform per launch and
-// are precomputed by the caller of philox_normal4.
+// are precomputed on the host (StepParams).
 // ---------------------------------------------------------------------------------
 struct PhiloxKeys {
     uint32_t k0[10], k1[10];
 };
 
-__device__ __forceinline__ PhiloxKeys philox_round_keys(uint32_t key0, uint32_t key1) {
+// What the kernel receives: the caller's launch block plus values bnnp_launch derives from
+// it on the host -- the ten Philox round keys and the fp32 roundings of the uniform
+// coefficients.  They sit in the constant bank and are used as instruction operands
+// directly (no registers, no per-round key arithmetic).
+struct StepParams {
+    BnnpLaunch L;
+    PhiloxKeys keys;
+    float cm, cn, gmax;
+};
+
+__host__ __device__ __forceinline__ PhiloxKeys philox_round_keys(uint32_t key0, uint32_t key1) {
     PhiloxKeys k;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -118,68 +128,64 @@ __device__ __forceinline__ void philox_normal4(uint64_t quad, uint64_t call, con
 // ---------------------------------------------------------------------------------
 // Priors.  Per-segment constants (uniform over the CTA).
 // ---------------------------------------------------------------------------------
-// The kernel evaluates five closed forms; the ten prior kinds of the ABI map onto them:
-//   F_NORMAL      Normal, LogNormal (= Normal in p plus the "- p" of prior/loc_scale.py:91)
+// The kernel evaluates six closed forms; the ten prior kinds of the ABI map onto them:
+//   F_NORMAL      Normal
+//   F_LOGNORMAL   LogNormal (= Normal in p plus the "- p" of prior/loc_scale.py:91)
 //   F_LAPLACE     Laplace
 //   F_STUDENT_T   StudentT, Cauchy (= StudentT with df = 1)
 //   F_GENNORM     GenNorm (prior/distributions.py:75-79)
 //   F_DOUBLE_GAMMA DoubleGamma (prior/transformed.py:83-96)
 //   F_NONE        no prior / Uniform / Improper: no gradient, a constant log density
-enum { F_NONE = 0, F_NORMAL, F_LAPLACE, F_STUDENT_T, F_GENNORM, F_DOUBLE_GAMMA };
+enum { F_NONE = 0, F_NORMAL, F_LOGNORMAL, F_LAPLACE, F_STUDENT_T, F_GENNORM, F_DOUBLE_GAMMA };
 
+// Only the constants a form reads are set by make_prior<FORM>; the rest stay dead, so the
+// common Normal case carries three floats (loc, k, inv_s) through the hot loop.
 struct PriorConst {
-    int form;       // F_*
     float loc;
-    float k;        // F_NORMAL: 1/(N s^2); F_LAPLACE: 1/(N s); others: 1/N
-    float c;        // F_NORMAL: the constant part of the gradient term (LogNormal: 1/N, else 0)
-    float lin;      // F_NORMAL: log density has "- lin * p" (LogNormal: 1, else 0)
+    float k;        // F_NORMAL / F_LOGNORMAL: 1/(N s^2); F_LAPLACE: 1/(N s); others: 1/N
+    float c;        // F_LOGNORMAL: the constant part of the gradient term, 1/N
     float a, b;     // F_STUDENT_T: a = df + 1, b = df s^2;  F_GENNORM: a = beta;  F_DOUBLE_GAMMA: a = conc - 1
     float la;       // F_STUDENT_T: -.5 (df + 1)
     float inv_s;    // 1/s
     float inv_df;
 };
 
+__device__ __forceinline__ int prior_form(int kind) {
+    switch (kind) {
+        case BNNP_PRIOR_NORMAL: return F_NORMAL;
+        case BNNP_PRIOR_LOGNORMAL: return F_LOGNORMAL;
+        case BNNP_PRIOR_LAPLACE: return F_LAPLACE;
+        case BNNP_PRIOR_STUDENT_T:
+        case BNNP_PRIOR_CAUCHY: return F_STUDENT_T;
+        case BNNP_PRIOR_GENNORM: return F_GENNORM;
+        case BNNP_PRIOR_DOUBLE_GAMMA: return F_DOUBLE_GAMMA;
+        default: return F_NONE;
+    }
+}
+
+template <int FORM>
 __device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double inv_n) {
     PriorConst pc;
-    const int kind = sd.prior_kind;
     pc.loc = sd.prior_loc;
     const float s = sd.prior_scale;
-    const float df = (kind == BNNP_PRIOR_CAUCHY) ? 1.0f : sd.prior_df;
     pc.inv_s = 1.0f / s;
-    pc.inv_df = 1.0f / df;
-    pc.a = df + 1.0f;
-    pc.b = df * s * s;
-    pc.la = -0.5f * (df + 1.0f);
-    pc.c = 0.0f;
-    pc.lin = 0.0f;
     pc.k = (float)inv_n;
-    switch (kind) {
-        case BNNP_PRIOR_LOGNORMAL:
-            pc.c = (float)inv_n;
-            pc.lin = 1.0f;
-            // fall through
-        case BNNP_PRIOR_NORMAL:
-            pc.form = F_NORMAL;
-            pc.k = (float)(inv_n / ((double)s * (double)s));
-            break;
-        case BNNP_PRIOR_LAPLACE:
-            pc.form = F_LAPLACE;
-            pc.k = (float)(inv_n / (double)s);
-            break;
-        case BNNP_PRIOR_STUDENT_T:
-        case BNNP_PRIOR_CAUCHY:
-            pc.form = F_STUDENT_T;
-            break;
-        case BNNP_PRIOR_GENNORM:
-            pc.form = F_GENNORM;
-            pc.a = sd.prior_df;            // beta
-            break;
-        case BNNP_PRIOR_DOUBLE_GAMMA:
-            pc.form = F_DOUBLE_GAMMA;
-            pc.a = sd.prior_df - 1.0f;     // concentration - 1
-            break;
-        default:
-            pc.form = F_NONE;
+    pc.c = pc.a = pc.b = pc.la = pc.inv_df = 0.0f;
+    if (FORM == F_NORMAL || FORM == F_LOGNORMAL) {
+        pc.k = (float)(inv_n / ((double)s * (double)s));
+        pc.c = (float)inv_n;
+    } else if (FORM == F_LAPLACE) {
+        pc.k = (float)(inv_n / (double)s);
+    } else if (FORM == F_STUDENT_T) {
+        const float df = (sd.prior_kind == BNNP_PRIOR_CAUCHY) ? 1.0f : sd.prior_df;
+        pc.inv_df = 1.0f / df;
+        pc.a = df + 1.0f;
+        pc.b = df * s * s;
+        pc.la = -0.5f * (df + 1.0f);
+    } else if (FORM == F_GENNORM) {
+        pc.a = sd.prior_df;            // beta
+    } else if (FORM == F_DOUBLE_GAMMA) {
+        pc.a = sd.prior_df - 1.0f;     // concentration - 1
     }
     return pc;
 }
@@ -189,7 +195,8 @@ __device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double i
 template <int FORM>
 __device__ __forceinline__ float prior_grad_term(const PriorConst& pc, float p) {
     const float d = p - pc.loc;
-    if (FORM == F_NORMAL) return fmaf(d, pc.k, pc.c);
+    if (FORM == F_NORMAL) return d * pc.k;
+    if (FORM == F_LOGNORMAL) return fmaf(d, pc.k, pc.c);
     if (FORM == F_LAPLACE) return d == 0.0f ? 0.0f : copysignf(pc.k, d);
     if (FORM == F_STUDENT_T) return (pc.a * d) / fmaf(d, d, pc.b) * pc.k;
     if (FORM == F_GENNORM) {            // beta |z|^(beta-1) sign(d) / (s N)
@@ -209,7 +216,8 @@ template <int FORM>
 __device__ __forceinline__ float log_prior_term(const PriorConst& pc, float p) {
     const float d = p - pc.loc;
     const float z = d * pc.inv_s;
-    if (FORM == F_NORMAL) return fmaf(-pc.lin, p, -0.5f * z * z);
+    if (FORM == F_NORMAL) return -0.5f * z * z;
+    if (FORM == F_LOGNORMAL) return -0.5f * z * z - p;
     if (FORM == F_LAPLACE) return -fabsf(z);
     if (FORM == F_STUDENT_T) return pc.la * log1pf(z * z * pc.inv_df);
     if (FORM == F_GENNORM) return -powf(fabsf(z), pc.a);
@@ -447,14 +455,20 @@ __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCt
 // The production variants (no replay buffer, at most the Verlet sums) are held to
 // BNNP_MIN_CTAS resident CTAs per SM; the metrics / replay variants need more
 // registers and would only spill under that cap.
-template <int NOISE, int SUMS>
+#ifndef BNNP_PRIOR_MIN_CTAS
+#define BNNP_PRIOR_MIN_CTAS BNNP_MIN_CTAS
+#endif
+template <int NOISE, int SUMS, bool PRIOR>
 constexpr int min_ctas() {
-    return (NOISE != BNNP_NOISE_REPLAY && SUMS != 2) ? BNNP_MIN_CTAS : (BNNP_MIN_CTAS > 3 ? 3 : BNNP_MIN_CTAS);
+    return (NOISE != BNNP_NOISE_REPLAY && SUMS != 2) ? (PRIOR ? BNNP_PRIOR_MIN_CTAS : BNNP_MIN_CTAS)
+                                                     : (BNNP_MIN_CTAS > 3 ? 3 : BNNP_MIN_CTAS);
 }
 
 template <int NOISE, bool PRIOR, bool NOISE_FIRST, int SUMS>
-__global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS>()) bnnp_step_kernel(const BnnpLaunch L) {
+__global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_step_kernel(const __grid_constant__ StepParams S) {
     __shared__ double s_red[NWARPS][BNNP_NRED];
+    const BnnpLaunch& L = S.L;
+    const PhiloxKeys& keys = S.keys;
 
     const int tid = threadIdx.x;
     const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[blockIdx.x] : (int)blockIdx.x;
@@ -472,17 +486,11 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS>()) bnnp_step_ke
     const uint32_t flags = L.flags;
 
     Coef c;
-    c.cm = (float)L.cm;
-    c.cn = (float)L.cn;
+    c.cm = S.cm;
+    c.cn = S.cn;
     c.cgM = (float)(L.cg * sd.precond);
     c.cpM = (float)(L.cp * sd.precond);
-    c.gmax = (float)L.grad_max;
-    PriorConst pc;
-    pc.form = F_NONE;
-    if (PRIOR) pc = make_prior(sd, L.inv_num_data);
-
-    PhiloxKeys keys;
-    if (NOISE == BNNP_NOISE_PHILOX) keys = philox_round_keys(L.key0, L.key1);
+    c.gmax = S.gmax;
 
     // ---- front-batched 128-bit loads: 3 (4 with replay noise) x UNROLL in flight per thread
     F4 p[UNROLL], g[UNROLL], m[UNROLL], z[UNROLL];
@@ -503,27 +511,25 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS>()) bnnp_step_ke
     for (int k = 0; k < BNNP_NRED; ++k) acc[k] = 0.0f;
 
     if (PRIOR) {
-        switch (pc.form) {   // uniform over the CTA: one closed form per segment
-            case F_NORMAL:
-                process_chunk<NOISE, true, F_NORMAL, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
-                break;
-            case F_LAPLACE:
-                process_chunk<NOISE, true, F_LAPLACE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
-                break;
-            case F_STUDENT_T:
-                process_chunk<NOISE, true, F_STUDENT_T, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
-                break;
-            case F_GENNORM:
-                process_chunk<NOISE, true, F_GENNORM, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
-                break;
-            case F_DOUBLE_GAMMA:
-                process_chunk<NOISE, true, F_DOUBLE_GAMMA, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
-                break;
-            default:
-                process_chunk<NOISE, true, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+#define BNNP_FORM_CASE(F)                                                                                      \
+    case F:                                                                                                    \
+        process_chunk<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, L.inv_num_data), keys, p, \
+                                                         g, m, z, acc);                                        \
+        break;
+        switch (prior_form(sd.prior_kind)) {   // uniform over the CTA: one closed form per segment
+            BNNP_FORM_CASE(F_NORMAL)
+#ifndef BNNP_ONLY_NORMAL
+            BNNP_FORM_CASE(F_LOGNORMAL)
+            BNNP_FORM_CASE(F_LAPLACE)
+            BNNP_FORM_CASE(F_STUDENT_T)
+            BNNP_FORM_CASE(F_GENNORM)
+            BNNP_FORM_CASE(F_DOUBLE_GAMMA)
+#endif
+            BNNP_FORM_CASE(F_NONE)
         }
+#undef BNNP_FORM_CASE
     } else {
-        process_chunk<NOISE, false, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, pc, keys, p, g, m, z, acc);
+        process_chunk<NOISE, false, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, PriorConst(), keys, p, g, m, z, acc);
     }
 
     // ---- chunk reduction: fp32 butterfly inside the warp, fp64 across warps (fixed order)
@@ -606,7 +612,7 @@ __global__ void __launch_bounds__(THREADS, BNNP_MIN_CTAS) bnnp_probe_stream_kern
     }
 }
 
-typedef void (*StepKernel)(const BnnpLaunch);
+typedef void (*StepKernel)(const StepParams);
 
 template <int NOISE, bool PRIOR, bool NF>
 StepKernel pick_sums(int sums) {
@@ -714,7 +720,13 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
     if (prior && !(f & BNNP_F_READ_P)) return fail(BNNP_E_ARG, "bnnp_launch: the prior needs READ_P");
     StepKernel k = pick_kernel(a->noise, prior, (f & BNNP_F_NOISE_FIRST) != 0, sums_needed(a->op, f));
     if (k == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: bad noise kind");
-    k<<<a->nchunks, THREADS, 0, (cudaStream_t)stream>>>(*a);
+    StepParams sp;
+    sp.L = *a;
+    sp.keys = philox_round_keys(a->key0, a->key1);
+    sp.cm = (float)a->cm;
+    sp.cn = (float)a->cn;
+    sp.gmax = (float)a->grad_max;
+    k<<<a->nchunks, THREADS, 0, (cudaStream_t)stream>>>(sp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "bnnp_step_kernel launch");
     return 0;
