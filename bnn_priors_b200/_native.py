@@ -81,6 +81,22 @@ class BnnpLaunch(C.Structure):
     ]
 
 
+# ---- include/bnnp_eval.h
+EVAL_CATEGORICAL, EVAL_NORMAL = 0, 1
+EV_LP_ENSEMBLE, EV_LP_LAST, EV_ACC_ENSEMBLE, EV_ACC_LAST, EV_LP_ENSEMBLE_CHECK = range(5)
+EV_OUT = 8
+EVAL_ROW = 5
+
+
+class BnnpEvalState(C.Structure):
+    _fields_ = [
+        ("ens", C.c_void_p), ("lps_lse", C.c_void_p), ("lps_last", C.c_void_p), ("acc_last", C.c_void_p),
+        ("rows", C.c_void_p), ("N", C.c_int64), ("C", C.c_int32), ("kind", C.c_int32),
+    ]
+
+
+EVAL_EXPORTS = ("bnnp_eval_batch", "bnnp_eval_finish", "bnnp_eval_last_error")
+
 EXPORTS = ("bnnp_abi_version", "bnnp_last_error", "bnnp_device_info", "bnnp_max_ctas_per_sm",
            "bnnp_plan_layout", "bnnp_launch", "bnnp_finalize", "bnnp_rollback", "bnnp_probe_stream")
 
@@ -112,7 +128,12 @@ def lib() -> C.CDLL:
     l.bnnp_finalize.argtypes = [C.POINTER(BnnpLaunch), C.c_void_p]
     l.bnnp_rollback.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
     l.bnnp_probe_stream.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
-    for name in EXPORTS:
+    l.bnnp_eval_batch.argtypes = [C.POINTER(BnnpEvalState), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    l.bnnp_eval_finish.argtypes = [C.POINTER(BnnpEvalState), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    l.bnnp_eval_last_error.restype = C.c_char_p
+    for name in EXPORTS + EVAL_EXPORTS:
         getattr(l, name)          # AttributeError if a symbol is missing
     if l.bnnp_abi_version() != ABI_VERSION:
         raise BnnpError(f"libbnnp.so has ABI {l.bnnp_abi_version()}, this package expects {ABI_VERSION}; rebuild")
@@ -123,6 +144,11 @@ def lib() -> C.CDLL:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise BnnpError(f"{what} failed ({rc}): {lib().bnnp_last_error().decode()}")
+
+
+def check_eval(rc: int, what: str) -> None:
+    if rc != 0:
+        raise BnnpError(f"{what} failed ({rc}): {lib().bnnp_eval_last_error().decode()}")
 
 
 def plan_layout(numels):

@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", "bnnp_kernels.cu")]
+SRC = [os.path.join(HERE, "csrc", "bnnp_kernels.cu"), os.path.join(HERE, "csrc", "bnnp_eval.cu")]
 INCLUDE = os.path.join(ROOT, "include")
 OUT = os.path.join(HERE, "_lib", "libbnnp.so")
 
@@ -33,7 +33,7 @@ def up_to_date() -> bool:
     if not os.path.exists(OUT):
         return False
     t = os.path.getmtime(OUT)
-    deps = SRC + [os.path.join(INCLUDE, "bnnp.h"), os.path.abspath(__file__)]
+    deps = SRC + [os.path.join(INCLUDE, "bnnp.h"), os.path.join(INCLUDE, "bnnp_eval.h"), os.path.abspath(__file__)]
     return all(os.path.getmtime(d) <= t for d in deps)
 
 

@@ -8,6 +8,11 @@ re-binds those three names -- on the already imported module object and in
 `sys.modules` -- so `experiments/train_bnn.py`, the runner classes and the reference's
 tests drive the kernels in this package without any change to the reference.
 
+`install(evaluate=True)` additionally re-binds `evaluate_model` (exp_utils.py:250-340;
+imported by name into inference.py:6 and inference_reject.py:6, reached as
+`exp_utils.evaluate_model` by experiments/train_bnn.py:148-149 and eval_bnn.py:62) to the
+device-side evaluation of `bnn_priors_b200.evaluate`.
+
     import bnn_priors_b200.overlay as overlay
     overlay.install()            # before or after `import bnn_priors`
     ...                          # run experiments/train_bnn.py's main, or a Runner
@@ -22,7 +27,24 @@ _NAMES = ("SGLD", "VerletSGLD", "HMC")
 _saved = {}
 
 
-def install(reference_package: str = "bnn_priors") -> None:
+_EVAL_MODULES = ("exp_utils", "inference", "inference_reject")
+
+
+def _install_evaluate(pkg: str) -> None:
+    from .evaluate import evaluate_model as fast_eval
+    saved = _saved.setdefault("evaluate", {})
+    for sub in _EVAL_MODULES:
+        name = f"{pkg}.{sub}"
+        try:
+            m = sys.modules.get(name) or importlib.import_module(name)
+        except ImportError:
+            continue                       # e.g. exp_utils needs h5py / sacred; nothing to patch then
+        if hasattr(m, "evaluate_model"):
+            saved.setdefault(sub, m.evaluate_model)
+            m.evaluate_model = fast_eval
+
+
+def install(reference_package: str = "bnn_priors", evaluate: bool = False) -> None:
     from . import mcmc as fast
     ref = importlib.import_module(reference_package + ".mcmc")
     if "classes" not in _saved:
@@ -37,6 +59,8 @@ def install(reference_package: str = "bnn_priors") -> None:
             _saved.setdefault("sub", {})[sub] = {n: getattr(m, n) for n in names}
             for n in names:
                 setattr(m, n, getattr(fast, n))
+    if evaluate:
+        _install_evaluate(reference_package)
 
 
 def uninstall() -> None:
@@ -50,4 +74,8 @@ def uninstall() -> None:
         m = sys.modules.get(f"{pkg}.mcmc.{sub}")
         for n, c in names.items():
             setattr(m, n, c)
+    for sub, fn in _saved.get("evaluate", {}).items():
+        m = sys.modules.get(f"{pkg}.{sub}")
+        if m is not None:
+            m.evaluate_model = fn
     _saved.clear()

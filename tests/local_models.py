@@ -183,6 +183,10 @@ class TinyClassifier(nn.Module):
     def log_prior(self):
         return sum(m.log_prob() for m in self.priors())
 
+    def forward(self, x):
+        "p(y | x, params) (models/base.py:37-40,179-180)"
+        return td.Categorical(logits=self.net(x))
+
     def log_likelihood_avg(self, x, y):
         return td.Categorical(logits=self.net(x)).log_prob(y).sum() / x.shape[0]
 
@@ -191,6 +195,17 @@ class TinyClassifier(nn.Module):
         log_prior = self.log_prior()
         potential_avg = loss - log_prior / eff_num_data
         return loss, log_prior, potential_avg
+
+
+class TinyRegressor(TinyClassifier):
+    "the shape of the reference's DenseNet (models/dense_nets.py:27-45): Normal(net(x), noise_std)"
+
+    def __init__(self, din, dout, width, noise_std=1.0):
+        super().__init__(din, dout, width)
+        self.noise_std = noise_std
+
+    def forward(self, x):
+        return td.Normal(self.net(x), self.noise_std)
 
 
 class GaussianTarget:

@@ -14,6 +14,7 @@ from bnn_priors_b200 import build as B
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = open(os.path.join(ROOT, "include", "bnnp.h")).read()
+EVAL_HEADER = open(os.path.join(ROOT, "include", "bnnp_eval.h")).read()
 
 
 @pytest.fixture(scope="module")
@@ -33,6 +34,41 @@ def test_every_declared_symbol_is_exported(lib):
     for n in names:
         assert getattr(lib, n) is not None
     assert lib.bnnp_abi_version() == N.ABI_VERSION
+
+
+def test_eval_header_symbols_constants_and_validation(lib):
+    body = re.sub(r"/\*.*?\*/", "", EVAL_HEADER, flags=re.S)
+    names = sorted(set(re.findall(r"\b(bnnp_[a-z_0-9]+)\s*\(", body)))
+    assert set(names) == set(N.EVAL_EXPORTS)
+    for n in names:
+        assert getattr(lib, n) is not None
+    assert int(re.search(r"#define\s+BNNP_EVAL_ROW\s+(\d+)", body).group(1)) == N.EVAL_ROW
+    for block in re.findall(r"enum\s*\{(.*?)\}", body, flags=re.S):
+        nxt = 0
+        for item in [x.strip() for x in block.split(",") if x.strip()]:
+            m = re.match(r"BNNP_([A-Z_0-9]+)\s*(?:=\s*(\d+))?$", item)
+            assert m, item
+            if m.group(2) is not None:
+                nxt = int(m.group(2))
+            assert getattr(N, m.group(1)) == nxt, m.group(1)
+            nxt += 1
+    fields = re.search(r"typedef struct BnnpEvalState \{(.*?)\} BnnpEvalState;", EVAL_HEADER, flags=re.S).group(1)
+    fields = re.sub(r"/\*.*?\*/", "", fields, flags=re.S)
+    got = [re.sub(r"^[A-Za-z_0-9]+\s*\**", "", d.strip(), count=1).strip() for d in fields.split(";") if d.strip()]
+    assert got == [f[0] for f in N.BnnpEvalState._fields_]
+    # argument validation happens before any CUDA call
+    st = N.BnnpEvalState()
+    assert lib.bnnp_eval_batch(C.byref(st), None, 0, None, None, None, 0, 0, 1, 0, None) == -1
+    assert b"bad state" in lib.bnnp_eval_last_error()
+    for f in ("ens", "lps_lse", "lps_last", "acc_last", "rows"):
+        setattr(st, f, 4096)
+    st.N, st.C, st.kind = 10, 3, N.EVAL_CATEGORICAL
+    assert lib.bnnp_eval_batch(C.byref(st), 4096, 3, None, 4096, None, 0, 8, 4, 0, None) == -1
+    assert b"outside the test set" in lib.bnnp_eval_last_error()
+    assert lib.bnnp_eval_batch(C.byref(st), 4096, 3, None, None, None, 0, 0, 4, 0, None) == -1
+    assert b"need labels" in lib.bnnp_eval_last_error()
+    assert lib.bnnp_eval_batch(C.byref(st), 4096, 3, None, 4096, None, 0, 0, 0, 0, None) == 0     # empty batch
+    assert lib.bnnp_eval_finish(C.byref(st), 4096, None, 0, 4096, None, None) == -1
 
 
 def test_python_constants_match_header():

@@ -104,3 +104,23 @@ def test_philox_normal_is_standard_normal():
     # different launch counters / keys decorrelate
     z2 = O.philox_normal(O.philox_key(7, 3), 12, np.arange(50000)).reshape(-1)
     assert abs(np.corrcoef(z, z2)[0, 1]) < 0.01
+
+
+# ---- test-set evaluation: oracle/eval_oracle.py against the reference's results
+@pytest.mark.parametrize("tag,kind", [("cls", 0), ("reg", 1)])
+def test_eval_oracle_reproduces_reference_results(tag, kind):
+    from oracle import eval_oracle as EO
+    z = np.load(os.path.join(GOLDEN_DIR, "eval.npz"))
+    want = json.loads(str(z[f"{tag}.results"]))
+    got = EO.evaluate(z[f"{tag}.acc_data"], z[f"{tag}.lps"], z[f"{tag}.y"], kind)
+    for k in ("lp_ensemble", "lp_last", "acc_ensemble", "acc_last"):
+        # the reference takes the accuracy mean in float32 (models/base.py:185): 1e-7
+        assert math.isclose(got[k], want[k], rel_tol=1e-7, abs_tol=1e-7), (k, got[k], want[k])
+    if kind == 0:
+        assert math.isclose(got["lp_ensemble_check"], got["lp_ensemble"], rel_tol=1e-6)
+        assert np.allclose(got["probs_mean"].sum(1), 1.0)
+    # a one-sample ensemble (the per-epoch call of the runners, inference.py:199-213)
+    want1 = json.loads(str(z[f"{tag}.results_last_only"]))
+    got1 = EO.evaluate(z[f"{tag}.acc_data"][-1:], z[f"{tag}.lps"][-1:], z[f"{tag}.y"], kind)
+    for k in ("lp_ensemble", "lp_last", "acc_ensemble", "acc_last"):
+        assert math.isclose(got1[k], want1[k], rel_tol=1e-7, abs_tol=1e-7), (k, got1[k], want1[k])

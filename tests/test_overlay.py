@@ -31,6 +31,17 @@ def test_overlay_rebinds_the_reference_samplers():
         finally:
             overlay.uninstall()
         assert ref_mcmc.VerletSGLD is original and inference.mcmc.SGLD is not fast.SGLD
+        # evaluate_model (exp_utils.py:250) as the runners and the experiment scripts reach it
+        from bnn_priors import exp_utils
+        from bnn_priors_b200.evaluate import evaluate_model as fast_eval
+        ref_eval = exp_utils.evaluate_model
+        overlay.install(evaluate=True)
+        try:
+            assert inference.evaluate_model is fast_eval and inference_reject.evaluate_model is fast_eval
+            assert exp_utils.evaluate_model is fast_eval
+        finally:
+            overlay.uninstall()
+        assert exp_utils.evaluate_model is ref_eval and inference.evaluate_model is ref_eval
     finally:
         sys.path.remove(REFERENCE)
         sys.path.remove(os.path.join(HERE, "golden", "_shims"))
