@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BNNP_LIB") or os.path.join(HERE, "_lib", "libbnnp.so")
 
 # ---- constants of include/bnnp.h (tests/test_abi.py checks them against the header)
-ABI_VERSION = 5
+ABI_VERSION = 6
 SEG_ALIGN = 32
 THREADS = 256
 UNROLL = 4
@@ -25,6 +25,7 @@ STATE_STRIDE = 16
 
 PRIOR_NONE, PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T = 0, 1, 2, 3
 PRIOR_CAUCHY, PRIOR_GENNORM, PRIOR_LOGNORMAL, PRIOR_UNIFORM, PRIOR_IMPROPER, PRIOR_DOUBLE_GAMMA = 4, 5, 6, 7, 8, 9
+PRIOR_HYPER_GAMMA, PRIOR_HYPER_UNIFORM, PRIOR_HYPER_HALFCAUCHY, PRIOR_HYPER_IMPROPER = 10, 11, 12, 13
 OP_SGLD, OP_VERLET, OP_HMC, OP_SAMPLE_MOMENTUM, OP_REDUCE = 0, 1, 2, 3, 4
 PHASE_INITIAL, PHASE_MID, PHASE_FINAL = 0, 1, 2
 NOISE_NONE, NOISE_REPLAY, NOISE_PHILOX = 0, 1, 2
@@ -43,16 +44,18 @@ F_MM_PRE_NOISE = 1 << 10
 F_UPDATE_SQ = 1 << 11
 F_PRIOR_GRAD = 1 << 12
 F_ALL_SUMS = 1 << 13
+F_HYPER = 1 << 14
 
 (S_DELTA_ENERGY, S_PREV_NEW_MOM, S_EST_MM, S_EST_PG, S_SUM_GG, S_SUM_MM, S_SQ_MEAN,
- S_LOG_PRIOR, S_GM_OLD, S_GM_NEW, S_MM_OLD, S_MM_NEW, S_NONFINITE, S_LAUNCHES) = range(14)
+ S_LOG_PRIOR, S_GM_OLD, S_GM_NEW, S_MM_OLD, S_MM_NEW, S_NONFINITE, S_LAUNCHES, S_HYPER) = range(15)
 
 # BnnpSegment as a numpy record (the table is built on the host and copied to HBM)
 SEGMENT_DTYPE = np.dtype([
     ("off", np.int64), ("numel", np.int64), ("precond", np.float64),
     ("prior_loc", np.float32), ("prior_scale", np.float32), ("prior_df", np.float32),
-    ("prior_kind", np.int32), ("first_chunk", np.int32), ("num_chunks", np.int32)], align=True)
-assert SEGMENT_DTYPE.itemsize == 48
+    ("prior_kind", np.int32), ("first_chunk", np.int32), ("num_chunks", np.int32),
+    ("link", np.int32), ("reserved", np.int32)], align=True)
+assert SEGMENT_DTYPE.itemsize == 56
 
 
 class BnnpEpilogue(C.Structure):
@@ -60,6 +63,7 @@ class BnnpEpilogue(C.Structure):
         ("valid", C.c_int32), ("op", C.c_int32), ("phase", C.c_int32), ("flags", C.c_uint32),
         ("parity", C.c_int32), ("reserved", C.c_int32), ("call", C.c_uint64),
         ("c_gm_base", C.c_double), ("curv_base", C.c_double), ("rms_alpha", C.c_double),
+        ("inv_num_data", C.c_double),
     ]
 
 

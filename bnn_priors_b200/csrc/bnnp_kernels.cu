@@ -136,7 +136,9 @@ __device__ __forceinline__ void philox_normal4(uint64_t quad, uint64_t call, con
 //   F_GENNORM     GenNorm (prior/distributions.py:75-79)
 //   F_DOUBLE_GAMMA DoubleGamma (prior/transformed.py:83-96)
 //   F_NONE        no prior / Uniform / Improper: no gradient, a constant log density
-enum { F_NONE = 0, F_NORMAL, F_LOGNORMAL, F_LAPLACE, F_STUDENT_T, F_GENNORM, F_DOUBLE_GAMMA };
+//   F_CONST       hyper segments (one element u): the gradient term -(1/N) dlog p/du was left in
+//                 the segment state by the epilogue of the BNNP_F_HYPER pre-pass
+enum { F_NONE = 0, F_NORMAL, F_LOGNORMAL, F_LAPLACE, F_STUDENT_T, F_GENNORM, F_DOUBLE_GAMMA, F_CONST };
 
 // Only the constants a form reads are set by make_prior<FORM>; the rest stay dead, so the
 // common Normal case carries three floats (loc, k, inv_s) through the hot loop.
@@ -159,12 +161,40 @@ __device__ __forceinline__ int prior_form(int kind) {
         case BNNP_PRIOR_CAUCHY: return F_STUDENT_T;
         case BNNP_PRIOR_GENNORM: return F_GENNORM;
         case BNNP_PRIOR_DOUBLE_GAMMA: return F_DOUBLE_GAMMA;
+        case BNNP_PRIOR_HYPER_GAMMA:
+        case BNNP_PRIOR_HYPER_UNIFORM:
+        case BNNP_PRIOR_HYPER_HALFCAUCHY:
+        case BNNP_PRIOR_HYPER_IMPROPER: return F_CONST;
         default: return F_NONE;
     }
 }
 
+__host__ __device__ __forceinline__ bool is_hyper_kind(int kind) {
+    return kind >= BNNP_PRIOR_HYPER_GAMMA && kind <= BNNP_PRIOR_HYPER_IMPROPER;
+}
+__host__ __device__ __forceinline__ bool may_have_hyper_scale(int kind) {
+    return kind == BNNP_PRIOR_NORMAL || kind == BNNP_PRIOR_LAPLACE || kind == BNNP_PRIOR_STUDENT_T;
+}
+
+// Hierarchical priors: scale s(u) of a hyper segment and ds/du, float64.
+//   softplus as torch.nn.functional.softplus (threshold 20): prior/transformed.py:57-58,74-75
+//   a + b Phi(u): prior/transformed.py:28-30
+__device__ __forceinline__ void hyper_scale(const BnnpSegment& h, double u, double& s, double& ds) {
+    const double a = (double)h.prior_loc, b = (double)h.prior_scale;
+    if (h.prior_kind == BNNP_PRIOR_HYPER_UNIFORM) {
+        s = a + b * (0.5 * erfc(-u * 0.7071067811865476));
+        ds = b * exp(-0.5 * u * u) * 0.3989422804014327;
+        return;
+    }
+    const double sp = u > 20.0 ? u : log1p(exp(u));
+    const double sg = u > 20.0 ? 1.0 : 1.0 / (1.0 + exp(-u));
+    const double mult = h.prior_kind == BNNP_PRIOR_HYPER_HALFCAUCHY ? b : 1.0;
+    s = sp * mult;
+    ds = sg * mult;
+}
+
 template <int FORM>
-__device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double inv_n) {
+__device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double inv_n, float hyper_term) {
     PriorConst pc;
     pc.loc = sd.prior_loc;
     const float s = sd.prior_scale;
@@ -186,6 +216,8 @@ __device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double i
         pc.a = sd.prior_df;            // beta
     } else if (FORM == F_DOUBLE_GAMMA) {
         pc.a = sd.prior_df - 1.0f;     // concentration - 1
+    } else if (FORM == F_CONST) {
+        pc.c = hyper_term;
     }
     return pc;
 }
@@ -207,6 +239,17 @@ __device__ __forceinline__ float prior_grad_term(const PriorConst& pc, float p) 
         const float sg = d == 0.0f ? 0.0f : copysignf(1.0f, d);
         return (sg * pc.inv_s - pc.a / d) * pc.k;
     }
+    if (FORM == F_CONST) return pc.c;
+    return 0.0f;
+}
+
+// the statistic of d log p / d scale a BNNP_F_HYPER launch reduces per linked segment
+template <int FORM>
+__device__ __forceinline__ float scale_stat_term(const PriorConst& pc, float p) {
+    const float d = p - pc.loc;
+    if (FORM == F_NORMAL) return d * d;
+    if (FORM == F_LAPLACE) return fabsf(d);
+    if (FORM == F_STUDENT_T) return (d * d) / fmaf(d, d, pc.b);
     return 0.0f;
 }
 
@@ -313,7 +356,11 @@ __device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c,
             acc[R_PG] = fmaf(p0, gj, acc[R_PG]);
         }
         const float pn = fmaf(c.cpM, t, p0);      // stored only with BNNP_F_WRITE_P
-        if (PRIOR && KIND != F_NONE) {
+        if (PRIOR && SUMS == SUMS_ALL && (KIND == F_NORMAL || KIND == F_LAPLACE || KIND == F_STUDENT_T)) {
+            // pre-pass of the hierarchical priors: g and m are not read, the slot is free
+            if ((flags & BNNP_F_HYPER) && j < valid) acc[R_GM_OLD] += scale_stat_term<KIND>(pc, p0);
+        }
+        if (PRIOR && KIND != F_NONE && KIND != F_CONST) {
             if ((flags & BNNP_F_LOG_PRIOR) && j < valid)
                 acc[R_LOGP] += log_prior_term<KIND>(pc, (flags & BNNP_F_WRITE_P) ? pn : p0);
         }
@@ -330,6 +377,52 @@ __host__ __device__ inline int sums_needed(int op, uint32_t flags) {
 
 // The reference's per-tensor scalar bookkeeping for one segment and one launch `E`,
 // applied to the segment-state array (fp64) from the eight folded sums `r`.
+// Epilogue of the hierarchical-prior pre-pass (BNNP_F_HYPER) for one segment.
+//   hyper segment h (link = weight segment w): from u = P[off_h] and the statistic T of w
+//   (folded into r[BNNP_NRED] by apply_pending):
+//     BNNP_S_LOG_PRIOR <- log density of the scale           (scale_prior.log_prob())
+//     BNNP_S_HYPER     <- -(1/N) d/du [ sum_i log p(w_i | s(u)) + log p_hyper(s(u)) ]
+//     segs[w].prior_scale <- s(u)                            (what scale_prior() returns)
+//   linked weight segment: its log-prior constant uses s(u); BNNP_S_HYPER <- T.
+__device__ void hyper_epilogue(const BnnpLaunch& L, const BnnpEpilogue& E, const BnnpSegment& sd, double* st,
+                               const double* r) {
+    if (sd.link < 0 || sd.link >= L.nseg) return;
+    if (is_hyper_kind(sd.prior_kind)) {
+        const BnnpSegment w = L.segs[sd.link];
+        const double u = (double)L.P[sd.off];
+        double s, ds;
+        hyper_scale(sd, u, s, ds);
+        const double a = (double)sd.prior_loc, b = (double)sd.prior_scale;
+        double lp = 0.0, dlp = 0.0;
+        if (sd.prior_kind == BNNP_PRIOR_HYPER_GAMMA) {               // td.Gamma(a, b).log_prob(s)
+            lp = a * log(b) + (a - 1.0) * log(s) - b * s - lgamma(a);
+            dlp = ((a - 1.0) / s - b) * ds;
+        } else if (sd.prior_kind == BNNP_PRIOR_HYPER_UNIFORM) {      // -log(high - low)
+            lp = -log(b);
+        } else if (sd.prior_kind == BNNP_PRIOR_HYPER_HALFCAUCHY) {   // td.HalfCauchy(a).log_prob(s)
+            const double q = s / a;
+            lp = -0.4515827052894548 /* log(2/pi) */ - log(a) - log1p(q * q);
+            dlp = -(2.0 * q / a) / (1.0 + q * q) * ds;
+        }
+        const double T = r[BNNP_NRED], n = (double)w.numel, df = (double)w.prior_df;
+        double dl_ds = 0.0;                                          // sum_i d log p(w_i | s) / ds
+        if (w.prior_kind == BNNP_PRIOR_NORMAL) dl_ds = T / (s * s * s) - n / s;
+        else if (w.prior_kind == BNNP_PRIOR_LAPLACE) dl_ds = T / (s * s) - n / s;
+        else if (w.prior_kind == BNNP_PRIOR_STUDENT_T) dl_ds = (df + 1.0) * T / s - n / s;
+        st[BNNP_S_LOG_PRIOR] = lp;
+        st[BNNP_S_HYPER] = -E.inv_num_data * (dl_ds * ds + dlp);
+        L.segs[sd.link].prior_scale = (float)s;
+    } else if (may_have_hyper_scale(sd.prior_kind)) {
+        const BnnpSegment h = L.segs[sd.link];
+        double s, ds;
+        hyper_scale(h, (double)L.P[h.off], s, ds);
+        BnnpSegment now = sd;
+        now.prior_scale = (float)s;
+        st[BNNP_S_LOG_PRIOR] = r[R_LOGP] + (double)sd.numel * log_prior_const(now);
+        st[BNNP_S_HYPER] = r[R_GM_OLD];
+    }
+}
+
 __device__ void segment_epilogue(const BnnpEpilogue& E, double* seg_state, const BnnpSegment& sd, int seg,
                                  const double* r) {
     const uint32_t flags = E.flags;
@@ -407,8 +500,21 @@ __device__ void apply_pending(const BnnpLaunch& L, const BnnpSegment& sd, int se
         t = warp_sum_f64(t);
         if (lane == 0) s_sum[k] = t;
     }
+    if ((E.flags & BNNP_F_HYPER) && is_hyper_kind(sd.prior_kind) && sd.link >= 0 && sd.link < L.nseg && warp == 0) {
+        // the statistic of the segment this hyper-parameter scales: fold that segment's records
+        // here, so that no CTA depends on another CTA's epilogue
+        const BnnpSegment w = L.segs[sd.link];
+        const double* base = L.partials + ((int64_t)E.parity * L.nchunks_total + w.first_chunk) * BNNP_NRED + R_GM_OLD;
+        double t = 0.0;
+        for (int ch = lane; ch < w.num_chunks; ch += 32) t += ld_cg_f64(base + (int64_t)ch * BNNP_NRED);
+        t = warp_sum_f64(t);
+        if (lane == 0) s_sum[BNNP_NRED] = t;
+    }
     __syncthreads();
-    if (tid == 0) segment_epilogue(E, L.seg_state, sd, seg, s_sum);
+    if (tid == 0) {
+        segment_epilogue(E, L.seg_state, sd, seg, s_sum);
+        if (E.flags & BNNP_F_HYPER) hyper_epilogue(L, E, sd, L.seg_state + (int64_t)seg * BNNP_STATE_STRIDE, s_sum);
+    }
     __syncthreads();   // s_sum is reused by the caller
 }
 
@@ -473,7 +579,7 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     const int tid = threadIdx.x;
     const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[blockIdx.x] : (int)blockIdx.x;
     const int seg = L.chunk_seg[chunk];
-    const BnnpSegment sd = L.segs[seg];
+    BnnpSegment sd = L.segs[seg];
     // the previous launch's bookkeeping: segment j is handled by CTA j, i.e. by the CTAs that
     // start first, so the few microseconds it takes are absorbed at the front of the launch
     if (L.pending.valid && (int)blockIdx.x < L.nseg) apply_pending(L, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
@@ -511,10 +617,22 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     for (int k = 0; k < BNNP_NRED; ++k) acc[k] = 0.0f;
 
     if (PRIOR) {
+        float hyper_term = 0.0f;
+        if (is_hyper_kind(sd.prior_kind)) {
+            // -(1/N) d log p / du, left by the epilogue of the BNNP_F_HYPER pre-pass (finalised before
+            // this launch started: bnnp_launch refuses a pending BNNP_F_HYPER epilogue)
+            hyper_term = (float)L.seg_state[(int64_t)seg * BNNP_STATE_STRIDE + BNNP_S_HYPER];
+        } else if ((flags & BNNP_F_HYPER) && sd.link >= 0 && sd.link < L.nseg && may_have_hyper_scale(sd.prior_kind)) {
+            // pre-pass: the scale is what the hyper-parameter now in P says (nobody writes P in this launch)
+            const BnnpSegment h = L.segs[sd.link];
+            double s, ds;
+            hyper_scale(h, (double)L.P[h.off], s, ds);
+            sd.prior_scale = (float)s;
+        }
 #define BNNP_FORM_CASE(F)                                                                                      \
     case F:                                                                                                    \
-        process_chunk<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, L.inv_num_data), keys, p, \
-                                                         g, m, z, acc);                                        \
+        process_chunk<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, L.inv_num_data, hyper_term), \
+                                                         keys, p, g, m, z, acc);                               \
         break;
         switch (prior_form(sd.prior_kind)) {   // uniform over the CTA: one closed form per segment
             BNNP_FORM_CASE(F_NORMAL)
@@ -525,6 +643,7 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
             BNNP_FORM_CASE(F_GENNORM)
             BNNP_FORM_CASE(F_DOUBLE_GAMMA)
 #endif
+            BNNP_FORM_CASE(F_CONST)
             BNNP_FORM_CASE(F_NONE)
         }
 #undef BNNP_FORM_CASE
@@ -559,7 +678,7 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
 
 // bnnp_finalize: the pending epilogue of every segment, nothing else
 __global__ void __launch_bounds__(THREADS) bnnp_finalize_kernel(const BnnpLaunch L) {
-    __shared__ double s_red[BNNP_NRED];
+    __shared__ double s_red[BNNP_NRED + 1];
     const int seg = blockIdx.x;
     apply_pending(L, L.segs[seg], seg, s_red);
 }
@@ -716,6 +835,14 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
     if (misaligned(a->P) || misaligned(a->G) || misaligned(a->M) || misaligned(a->prev_p) || misaligned(a->prev_g) ||
         misaligned(a->prev_m) || misaligned(a->replay_noise))
         return fail(BNNP_E_ALIGN, "bnnp_launch: flat arrays must be 16-byte aligned");
+    if (a->pending.valid && (a->pending.flags & BNNP_F_HYPER))
+        return fail(BNNP_E_ARG, "bnnp_launch: the epilogue of a BNNP_F_HYPER launch rewrites the segment table; "
+                                "bnnp_finalize first");
+    if ((f & BNNP_F_HYPER) &&
+        (a->op != BNNP_OP_REDUCE || (f & (BNNP_F_WRITE_P | BNNP_F_PRIOR_GRAD)) || !(f & BNNP_F_LOG_PRIOR) ||
+         !(f & BNNP_F_READ_P) || a->chunk_ids != nullptr))
+        return fail(BNNP_E_ARG, "bnnp_launch: BNNP_F_HYPER is the read-only pre-pass: BNNP_OP_REDUCE over all "
+                                "chunks with READ_P | LOG_PRIOR, no WRITE_P / PRIOR_GRAD");
     const bool prior = (f & (BNNP_F_LOG_PRIOR | BNNP_F_PRIOR_GRAD)) != 0;
     if (prior && !(f & BNNP_F_READ_P)) return fail(BNNP_E_ARG, "bnnp_launch: the prior needs READ_P");
     StepKernel k = pick_kernel(a->noise, prior, (f & BNNP_F_NOISE_FIRST) != 0, sums_needed(a->op, f));
@@ -737,6 +864,8 @@ int bnnp_finalize(const BnnpLaunch* a, void* stream) {
     if (!a->pending.valid) return 0;
     if (a->nseg <= 0 || a->segs == nullptr || a->seg_state == nullptr || a->partials == nullptr || a->stamps == nullptr)
         return fail(BNNP_E_ARG, "bnnp_finalize: null table pointer");
+    if ((a->pending.flags & BNNP_F_HYPER) && a->P == nullptr)
+        return fail(BNNP_E_ARG, "bnnp_finalize: the epilogue of a BNNP_F_HYPER launch reads P");
     if ((a->pending.parity | 1) != 1) return fail(BNNP_E_ARG, "bnnp_finalize: parity must be 0 or 1");
     bnnp_finalize_kernel<<<a->nseg, THREADS, 0, (cudaStream_t)stream>>>(*a);
     cudaError_t e = cudaGetLastError();

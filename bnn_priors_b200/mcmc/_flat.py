@@ -152,6 +152,7 @@ class FlatGroup:
         self.table["precond"] = 1.0
         self.table["prior_scale"], self.table["prior_df"] = 1.0, 3.0
         self.table["first_chunk"], self.table["num_chunks"] = first, nch
+        self.table["link"] = -1
         self.table_dev = torch.empty(self.table.nbytes, dtype=torch.uint8, device=dev)
         self._table_dirty = True
         self.chunk_seg_host = np.ascontiguousarray(chunk_seg)
@@ -195,6 +196,10 @@ class FlatGroup:
         self.grad_max: Optional[float] = None
         self._lp_valid = False
         self._lp_pversion = None
+        # hierarchical priors: {hyper segment: weight segment}; see hyper_prepass
+        self.hyper_links = {}
+        self._hyper_valid = False
+        self._hyper_pversion = None
         # validity of SUM_GG / SUM_MM in the segment state
         self._gg_version = None
         self._mm_version = None
@@ -231,7 +236,12 @@ class FlatGroup:
         for p, gv, pv, ptr in self._sync_rows:
             g = p.grad
             if g is not gv:
-                if g is None:
+                if g is None and i in self.hyper_links:
+                    # a fused hyper-parameter reaches the loss only through the prior, which is no
+                    # longer in autograd: its likelihood gradient is zero
+                    gv.zero_()
+                    p.grad = gv
+                elif g is None:
                     if raise_on_no_grad:
                         raise RuntimeError(f"No gradient for parameter with shape {p.shape}")
                     missing.append(i)
@@ -314,12 +324,51 @@ class FlatGroup:
         self._table_dirty = True
         self._lp_valid = False
 
+    def set_hyper_link(self, weight: int, hyper: int, kind: int, a: float, b: float) -> None:
+        """Segment `hyper` (one element u) holds the scale of segment `weight`
+        (include/bnnp.h: BNNP_PRIOR_HYPER_*; prior/hierarchical.py, prior/empirical_bayes.py)."""
+        t = self.table
+        if self.numel[hyper] != 1:
+            raise ValueError("a hyper-parameter segment has exactly one element")
+        if int(t["prior_kind"][weight]) not in (N.PRIOR_NORMAL, N.PRIOR_LAPLACE, N.PRIOR_STUDENT_T):
+            raise ValueError("only Normal / Laplace / StudentT segments can have a sampled scale")
+        t["prior_kind"][hyper], t["prior_loc"][hyper], t["prior_scale"][hyper] = kind, a, b
+        t["link"][hyper], t["link"][weight] = weight, hyper
+        self.hyper_links[hyper] = weight
+        self._table_dirty = True
+        self._lp_valid = self._hyper_valid = False
+
+    def clear_hyper_links(self) -> None:
+        for h, w in self.hyper_links.items():
+            self.table["link"][h] = self.table["link"][w] = -1
+        self.hyper_links = {}
+        self._table_dirty = True
+        self._lp_valid = self._hyper_valid = False
+
+    @property
+    def has_hyper(self) -> bool:
+        return bool(self.hyper_links)
+
+    def hyper_fresh(self) -> bool:
+        return self._hyper_valid and not self._table_dirty and self._hyper_pversion == self._p_version()
+
+    def hyper_prepass(self, inv_num_data: float) -> None:
+        """The read-only pre-pass of the hierarchical priors (BNNP_F_HYPER) followed by its
+        epilogue: afterwards the segment table holds the current scales s(u), the state holds
+        every segment's log-prior and, per hyper segment, -(1/N) dlog p/du."""
+        self.launch(N.OP_REDUCE, N.PHASE_MID, N.F_READ_P | N.F_LOG_PRIOR | N.F_HYPER, N.NOISE_NONE,
+                    cm=1.0, inv_num_data=inv_num_data)
+        self.flush_pending()
+        self._hyper_valid = self._lp_valid = True
+        self._hyper_pversion = self._lp_pversion = self._p_version()
+
     def _upload_table(self) -> None:
         # rare (preconditioner / prior changes): a plain blocking copy of a few KB.  The pending
         # epilogue still needs the OLD table (it reads the preconditioner), so it runs first.
         self.flush_pending()
         self.table_dev.copy_(torch.from_numpy(self.table.view(np.uint8).copy()))
         self._table_dirty = False
+        self._hyper_valid = False       # the device copy of the linked scales is the host's stale one again
 
     # ------------------------------------------------------------ scalars
     def poke(self, i: int, col: int, v: float) -> None:
@@ -377,7 +426,7 @@ class FlatGroup:
             e.valid = 0
         else:
             (e.valid, e.op, e.phase, e.flags, e.parity, e.call,
-             e.c_gm_base, e.curv_base, e.rms_alpha) = (1,) + pend
+             e.c_gm_base, e.curv_base, e.rms_alpha, e.inv_num_data) = (1,) + pend
 
     def _issue(self, a) -> None:
         """bnnp_launch with this chain's deferred-epilogue protocol: the launch carries the
@@ -391,7 +440,8 @@ class FlatGroup:
         else:
             rc = self.lib.bnnp_launch(C.byref(a), self._stream())
         N.check(rc, "bnnp_launch")
-        self._pending = (a.op, a.phase, a.flags, self._parity, self.call, a.c_gm_base, a.curv_base, a.rms_alpha)
+        self._pending = (a.op, a.phase, a.flags, self._parity, self.call, a.c_gm_base, a.curv_base, a.rms_alpha,
+                         a.inv_num_data)
         self._parity ^= 1
         self.call += 1
         self._epoch += 1
@@ -484,10 +534,12 @@ class FlatGroup:
             self._lp_pversion = self._p_version()
         elif flags & N.F_WRITE_P:
             self._lp_valid = False
+        if flags & N.F_WRITE_P:
+            self._hyper_valid = False
 
     def invalidate_sums(self) -> None:
         self._gg_version = self._mm_version = None
-        self._lp_valid = False
+        self._lp_valid = self._hyper_valid = False
 
     def reduce_now(self, inv_num_data: float) -> None:
         """dot(g,g), dot(m,m) and the log-prior of the CURRENT arrays (no writes)."""
@@ -495,13 +547,19 @@ class FlatGroup:
         if self.M is not None:
             flags |= N.F_READ_M
         if self.prior_fused:
-            flags |= N.F_READ_P | N.F_PRIOR_GRAD | N.F_LOG_PRIOR
+            flags |= N.F_READ_P | N.F_PRIOR_GRAD
+            if self.has_hyper:
+                # scales, hyper gradients and the log-prior come from the pre-pass
+                if not self.hyper_fresh():
+                    self.hyper_prepass(inv_num_data)
+            else:
+                flags |= N.F_LOG_PRIOR
             if self.grad_max is not None:
                 flags |= N.F_CLAMP_GRAD
         self.launch(N.OP_REDUCE, N.PHASE_MID, flags, N.NOISE_NONE, cm=1.0, inv_num_data=inv_num_data)
         self._gg_version = self.G._version
         self._mm_version = self.M._version if self.M is not None else None
-        if self.prior_fused:
+        if self.prior_fused and not self.has_hyper:
             self._lp_valid = True
             self._lp_pversion = self._p_version()
 

@@ -65,7 +65,7 @@ class HMC(VerletSGLD):
             flags |= N.F_SAVE_STATE
         if not is_final:
             flags |= N.F_WRITE_P | N.F_UPDATE_SQ
-            if pf:
+            if pf and not fg.has_hyper:
                 flags |= N.F_LOG_PRIOR
         fg.launch(self._OP, self._phase(is_initial, is_final), flags, N.NOISE_NONE,
                   cm=1.0, cg=-.5 * group['grad_v'] * group['bhn'], cn=0.0, cp=group['bh'],

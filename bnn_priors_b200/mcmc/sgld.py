@@ -185,6 +185,10 @@ class SGLD(torch.optim.Optimizer):
         f = N.F_PRIOR_GRAD
         if fg.grad_max is not None:
             f |= N.F_CLAMP_GRAD
+        if fg.has_hyper and not fg.hyper_fresh():
+            # hierarchical priors: current scales and -(1/N) dlog p/du come from a read-only
+            # pre-pass (free if model.log_prior() already ran it for these parameters)
+            fg.hyper_prepass(1.0 / group['num_data'])
         return f, 1.0 / group['num_data']
 
     def _step_fn(self, group, fg: FlatGroup, chunks, calc_metrics=True, is_final=False):
@@ -215,7 +219,7 @@ class SGLD(torch.optim.Optimizer):
             flags |= N.F_WRITE_P | N.F_UPDATE_SQ
             if a > 0:
                 flags |= N.F_WRITE_M
-            if pf:
+            if pf and not fg.has_hyper:
                 flags |= N.F_LOG_PRIOR
             noise = fg.take_noise_mode(group['temperature'] > 0)
             fg.launch(self._OP, N.PHASE_MID, flags, noise,

@@ -154,7 +154,7 @@ class VerletSGLD(SGLD):
             flags |= N.F_SAVE_STATE
         if not is_final:
             flags |= N.F_WRITE_P | N.F_UPDATE_SQ
-            if pf:
+            if pf and not fg.has_hyper:
                 flags |= N.F_LOG_PRIOR
         # the reference draws randn_like(p) even when noise_std == 0 (:163); a replayed
         # trace carries that draw, the Philox stream simply skips it

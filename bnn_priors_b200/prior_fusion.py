@@ -19,10 +19,15 @@ closed form:
     (inference_reject.py:20-22).
 
 Covered: Normal, Laplace, StudentT (the north star's three) and, as the next row of the
-scope table, Cauchy, GenNorm, LogNormal, Uniform, Improper and DoubleGamma,
-all with constant hyper-parameters.  Everything else (hierarchical, empirical-Bayes,
-mixtures, correlated and multivariate priors, Gamma / HalfCauchy on softplus) is left alone:
-their log_prob stays in autograd and their gradient arrives in p.grad as before.
+scope table, Cauchy, GenNorm, LogNormal, Uniform, Improper and DoubleGamma
+with constant hyper-parameters, plus Normal / Laplace / StudentT whose SCALE is a sampled
+scalar with a Gamma, Uniform, HalfCauchy or improper hyper-prior (prior/hierarchical.py:
+NormalGamma, NormalUniform, Horseshoe, LaplaceGamma, LaplaceUniform, StudentTGamma,
+StudentTUniform; prior/empirical_bayes.py: NormalEmpirical, LaplaceEmpirical).  For those the
+sampler runs a read-only pre-pass before a step (FlatGroup.hyper_prepass) that yields the
+current scale, the log-prior and the hyper-parameter's gradient on the device.
+Everything else (sampled df / beta, mixtures, correlated and multivariate priors) is left
+alone: their log_prob stays in autograd and their gradient arrives in p.grad as before.
 `p.grad` of a fused tensor holds the LIKELIHOOD gradient only.
 """
 from __future__ import annotations
@@ -97,6 +102,108 @@ def describe_prior(m: torch.nn.Module) -> Optional[tuple]:
     if loc is None or scale is None or t is None or not scale > 0 or not t > 0:
         return None
     return kind, loc, scale, t
+
+
+_HYPER_TARGETS = {td.Normal: N.PRIOR_NORMAL, td.Laplace: N.PRIOR_LAPLACE, td.StudentT: N.PRIOR_STUDENT_T}
+
+
+def _definer(cls, name):
+    return next((k.__name__ for k in cls.__mro__ if name in k.__dict__), None)
+
+
+def describe_hyper(h: torch.nn.Module) -> Optional[tuple]:
+    """(hyper kind, a, b) if `h` is a scalar scale prior the kernel knows: the reference's
+    Gamma / HalfCauchy (softplus-transformed, prior/transformed.py:50-80), Uniform (Gaussian
+    CDF-transformed, :12-47) or PositiveImproper (prior/loc_scale.py:100-103); else None."""
+    if not _is_prior_module(h) or h.p.numel() != 1:
+        return None
+    cls, keys = type(h), set(h.kwargs_keys)
+    lp_def, fw_def = _definer(cls, "log_prob"), _definer(cls, "forward")
+    dist = getattr(cls, "_dist", None)
+    if lp_def == "Gamma" and fw_def == "Gamma" and dist is td.Gamma and keys == {"concentration", "rate"}:
+        a, b = _constant(h, "concentration"), _constant(h, "rate")
+        return (N.PRIOR_HYPER_GAMMA, a, b) if a and b and a > 0 and b > 0 else None
+    if lp_def == "Uniform" and fw_def == "Uniform" and dist is td.Uniform and keys == {"low", "high"}:
+        lo, hi = _constant(h, "low"), _constant(h, "high")
+        return (N.PRIOR_HYPER_UNIFORM, lo, hi - lo) if lo is not None and hi is not None and hi > lo >= 0 else None
+    if lp_def == "HalfCauchy" and fw_def == "HalfCauchy" and dist is td.HalfCauchy and keys == {"scale"}:
+        a, mult = _constant(h, "scale"), getattr(h, "multiplier", None)
+        ok = a is not None and a > 0 and isinstance(mult, (int, float)) and mult > 0
+        return (N.PRIOR_HYPER_HALFCAUCHY, a, float(mult)) if ok else None
+    if lp_def == "Improper" and fw_def == "PositiveImproper":
+        return N.PRIOR_HYPER_IMPROPER, 0.0, 1.0
+    return None
+
+
+def describe_hier_prior(m: torch.nn.Module) -> Optional[tuple]:
+    """(kind, loc, df, hyper module, hyper kind, a, b) if `m` is a Normal / Laplace / StudentT
+    prior (base `Prior.log_prob`) whose `scale` is a recognised scalar prior module and whose
+    other hyper-parameters are constants; else None."""
+    cls = type(m)
+    if _definer(cls, "log_prob") != "Prior":
+        return None
+    kind = _HYPER_TARGETS.get(getattr(cls, "_dist", None))
+    keys = set(getattr(m, "kwargs_keys", ()))
+    if kind is None or keys != {"loc", "scale"} | ({"df"} if kind == N.PRIOR_STUDENT_T else set()):
+        return None
+    h = m._modules.get("scale")
+    loc = _constant(m, "loc")
+    df = _constant(m, "df") if kind == N.PRIOR_STUDENT_T else 3.0
+    hyper = describe_hyper(h) if h is not None else None
+    if hyper is None or loc is None or df is None or not df > 0:
+        return None
+    return (kind, loc, df, h) + hyper
+
+
+def hyper_closed_form(hkind: int, u: float, a: float, b: float):
+    "(s, ds/du, log density of s, d/du of it) in float64: csrc/bnnp_kernels.cu hyper_scale / hyper_epilogue"
+    if hkind == N.PRIOR_HYPER_UNIFORM:
+        s = a + b * 0.5 * math.erfc(-u / math.sqrt(2.0))
+        ds = b * math.exp(-0.5 * u * u) / math.sqrt(2.0 * math.pi)
+        return s, ds, -math.log(b), 0.0
+    sp = u if u > 20.0 else math.log1p(math.exp(u))
+    sg = 1.0 if u > 20.0 else 1.0 / (1.0 + math.exp(-u))
+    if hkind == N.PRIOR_HYPER_GAMMA:
+        return sp, sg, a * math.log(b) + (a - 1) * math.log(sp) - b * sp - math.lgamma(a), ((a - 1) / sp - b) * sg
+    if hkind == N.PRIOR_HYPER_HALFCAUCHY:
+        s, ds = sp * b, sg * b
+        q = s / a
+        return s, ds, math.log(2 / math.pi) - math.log(a) - math.log1p(q * q), -(2 * q / a) / (1 + q * q) * ds
+    if hkind == N.PRIOR_HYPER_IMPROPER:
+        return sp, sg, 0.0, 0.0
+    raise ValueError(hkind)
+
+
+def matches_hier_module(m: torch.nn.Module, spec: tuple, rtol: float = 1e-4) -> bool:
+    """Do the kernel's closed forms reproduce log_prob() + scale.log_prob() of `m` and the
+    autograd gradients w.r.t. the weights and the hyper-parameter at the current values?"""
+    kind, loc, df, h, hkind, a, b = spec
+    with torch.enable_grad():
+        lp = m.log_prob() + h.log_prob()
+        g_p, g_u = torch.autograd.grad(lp, [m.p, h.p], allow_unused=True)
+    g_u = 0.0 if g_u is None else float(g_u)
+    s, ds, lph, dlph = hyper_closed_form(hkind, float(h.p.detach()), a, b)
+    if abs(float(h().detach()) - s) > rtol * s:
+        return False
+    want_lp, want_g = closed_form(kind, m.p, loc, s, df)
+    d = m.p.detach().double() - loc
+    n = d.numel()
+    if kind == N.PRIOR_NORMAL:
+        dl_ds = float((d * d).sum()) / s ** 3 - n / s
+    elif kind == N.PRIOR_LAPLACE:
+        dl_ds = float(d.abs().sum()) / s ** 2 - n / s
+    else:
+        dl_ds = (df + 1) * float((d * d / (df * s * s + d * d)).sum()) / s - n / s
+    want_u = dl_ds * ds + dlph
+    lp = float(lp.detach())
+    if not (math.isfinite(lp) and math.isfinite(g_u) and bool(torch.isfinite(g_p).all())):
+        return False
+    if abs(lp - (float(want_lp) + lph)) > rtol * max(1.0, abs(lp)):
+        return False
+    if abs(g_u - want_u) > rtol * max(1.0, abs(g_u)):
+        return False
+    scale = float(g_p.double().abs().mean()) + 1e-30
+    return bool(((g_p.double() - want_g).abs() <= rtol * (g_p.double().abs() + scale)).all())
 
 
 def closed_form(kind: int, p: torch.Tensor, loc: float, scale: float, third: float):
@@ -184,8 +291,21 @@ class FusedPrior:
             for i, p in enumerate(fg.params):
                 where[id(p)] = (gi, i)
         self.groups = set()
+        hyper_done = set()           # scale priors fused together with their parent (visited after it)
         for _, m in model.named_modules():
-            if not _is_prior_module(m):
+            if not _is_prior_module(m) or id(m) in hyper_done:
+                continue
+            hier = describe_hier_prior(m)
+            if hier is not None and id(m.p) in where and id(hier[3].p) in where \
+                    and where[id(m.p)][0] == where[id(hier[3].p)][0] and (not verify or matches_hier_module(m, hier)):
+                kind, loc, df, h, hkind, a, b = hier
+                gi, i = where[id(m.p)]
+                fg = sampler.flat_groups[gi]
+                fg.set_prior(i, kind, loc, float(h().detach()), df)
+                fg.set_hyper_link(i, where[id(h.p)][1], hkind, a, b)
+                self.groups.add(gi)
+                self.fused_modules += [m, h]
+                hyper_done.add(id(h))
                 continue
             spec = describe_prior(m)
             if spec is not None and verify and not matches_module(m, spec):
@@ -213,9 +333,14 @@ class FusedPrior:
         total = None
         for gi in sorted(self.groups):
             fg = self.sampler.flat_groups[gi]
-            if not fg.log_prior_fresh():
+            inv_n = 1.0 / self.sampler.param_groups[gi]['num_data']
+            if fg.has_hyper:
+                if not (fg.hyper_fresh() and fg.log_prior_fresh()):
+                    fg.sync_views(raise_on_no_grad=False)
+                    fg.hyper_prepass(inv_n)       # scales, log-prior and hyper gradients in one read of P
+            elif not fg.log_prior_fresh():
                 fg.sync_views(raise_on_no_grad=False)
-                fg.reduce_now(1.0 / self.sampler.param_groups[gi]['num_data'])
+                fg.reduce_now(inv_n)
             fg.flush_pending()          # the sum lives in the segment state once the last launch's epilogue ran
             v = fg.state_dev[:, N.S_LOG_PRIOR].sum()
             total = v if total is None else total + v
@@ -229,6 +354,7 @@ class FusedPrior:
             fg = self.sampler.flat_groups[gi]
             for i in range(fg.nseg):
                 fg.set_prior(i, N.PRIOR_NONE, 0.0, 1.0, 3.0)
+            fg.clear_hyper_links()
             fg.prior_fused = False
             fg.grad_max = None
             fg.invalidate_sums()

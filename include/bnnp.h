@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BNNP_ABI_VERSION 5
+#define BNNP_ABI_VERSION 6
 
 #define BNNP_SEG_ALIGN 32      /* floats: every segment starts on a 128-byte line */
 #ifndef BNNP_THREADS
@@ -56,11 +56,27 @@ enum { BNNP_E_ARG = -1, BNNP_E_ALIGN = -2, BNNP_E_UNSUPPORTED = -3 };
  *   LOGNORMAL    loc, scale, -          prior/loc_scale.py:86-92 (density of p, incl. "- p")
  *   UNIFORM      low, high - low, -     prior/transformed.py:12-47 (constant density of p)
  *   IMPROPER     -, -, -                prior/loc_scale.py:94-97 (log_prob == 0)
- *   DOUBLE_GAMMA loc, scale, concentration   prior/transformed.py:83-96 */
+ *   DOUBLE_GAMMA loc, scale, concentration   prior/transformed.py:83-96
+ *
+ * Hierarchical priors (prior/hierarchical.py, prior/empirical_bayes.py): the scale of a
+ * NORMAL / LAPLACE / STUDENT_T segment may be a sampled scalar.  That scalar u is a segment
+ * of its own (numel 1, a "hyper segment") whose kind says how the scale s follows from u and
+ * which density s has; (prior_loc, prior_scale) hold its two constants (a, b); the two
+ * segments name each other in BnnpSegment.link:
+ *   HYPER_GAMMA      s = softplus(u),     s ~ Gamma(concentration a, rate b)
+ *                    prior/transformed.py:50-63; NormalGamma, LaplaceGamma, StudentTGamma
+ *   HYPER_UNIFORM    s = a + b Phi(u),    s ~ Uniform(a, a + b)
+ *                    prior/transformed.py:12-47; NormalUniform, LaplaceUniform, StudentTUniform
+ *   HYPER_HALFCAUCHY s = softplus(u) b,   s ~ HalfCauchy(scale a)
+ *                    prior/transformed.py:66-80; Horseshoe
+ *   HYPER_IMPROPER   s = softplus(u),     log density 0
+ *                    prior/loc_scale.py:100-103; NormalEmpirical, LaplaceEmpirical */
 enum {
     BNNP_PRIOR_NONE = 0, BNNP_PRIOR_NORMAL = 1, BNNP_PRIOR_LAPLACE = 2, BNNP_PRIOR_STUDENT_T = 3,
     BNNP_PRIOR_CAUCHY = 4, BNNP_PRIOR_GENNORM = 5, BNNP_PRIOR_LOGNORMAL = 6, BNNP_PRIOR_UNIFORM = 7,
-    BNNP_PRIOR_IMPROPER = 8, BNNP_PRIOR_DOUBLE_GAMMA = 9
+    BNNP_PRIOR_IMPROPER = 8, BNNP_PRIOR_DOUBLE_GAMMA = 9,
+    BNNP_PRIOR_HYPER_GAMMA = 10, BNNP_PRIOR_HYPER_UNIFORM = 11, BNNP_PRIOR_HYPER_HALFCAUCHY = 12,
+    BNNP_PRIOR_HYPER_IMPROPER = 13
 };
 
 /* which sampler's bookkeeping the per-segment epilogue applies */
@@ -95,10 +111,21 @@ enum {
     BNNP_F_UPDATE_SQ = 1u << 11,    /* square_avg moving average, sgld.py:153-154    */
     BNNP_F_PRIOR_GRAD = 1u << 12,   /* g <- g - (1/N) dlog p/dtheta in-register: models/
                                        base.py:72-77 + inference.py:218 without autograd */
-    BNNP_F_ALL_SUMS = 1u << 13      /* reduce every dot product even without CALC_METRICS
+    BNNP_F_ALL_SUMS = 1u << 13,     /* reduce every dot product even without CALC_METRICS
                                        (HMC initial/final need m.m: hmc.py:50-53,32-33);
                                        otherwise a launch only reduces what its epilogue
                                        reads: g.g always, g.m and g.m' for VERLET       */
+    BNNP_F_HYPER = 1u << 14         /* the hierarchical-prior pre-pass (BNNP_OP_REDUCE with
+                                       READ_P | LOG_PRIOR, no writes to P): linked segments
+                                       take their scale from the hyper-parameter u now in P,
+                                       the launch reduces sum log p and the statistic of
+                                       d log p / d scale, and its epilogue -- which must be
+                                       applied with bnnp_finalize before the next launch --
+                                       leaves, per hyper segment, the new scale in the segment
+                                       table, -(1/N) d log p / du in BNNP_S_HYPER and the
+                                       hyper log-density in BNNP_S_LOG_PRIOR.  Replaces
+                                       autograd through scale_prior() (prior/base.py:52-58,
+                                       prior/transformed.py:57-63)                      */
 };
 
 /* noise source */
@@ -119,7 +146,11 @@ enum {
     BNNP_S_MM_OLD = 10,
     BNNP_S_MM_NEW = 11,
     BNNP_S_NONFINITE = 12,     /* 1.0 if the gradient had a non-finite entry  */
-    BNNP_S_LAUNCHES = 13       /* number of launches that finalised this segment */
+    BNNP_S_LAUNCHES = 13,      /* number of launches that finalised this segment */
+    BNNP_S_HYPER = 14          /* hyper segment: -(1/N) d log p / du, added to its gradient
+                                  by launches with BNNP_F_PRIOR_GRAD; linked weight segment:
+                                  the statistic of d log p / d scale (sum d^2, sum |d|, sum
+                                  d^2 / (df s^2 + d^2))                                    */
 };
 
 /* One parameter tensor.  A table of these lives in device memory. */
@@ -132,6 +163,10 @@ typedef struct BnnpSegment {
     int32_t prior_kind;
     int32_t first_chunk; /* index of this segment's first chunk                */
     int32_t num_chunks;  /* ceil(numel / BNNP_CHUNK)                           */
+    int32_t link;        /* hierarchical priors: index of the hyper segment that holds
+                            this segment's scale, or (for a hyper segment) of the
+                            segment it scales; -1: none                         */
+    int32_t reserved;
 } BnnpSegment;
 
 /* What the per-segment scalar bookkeeping (the "epilogue") of a launch needs.  It is
@@ -146,6 +181,7 @@ typedef struct BnnpEpilogue {
     int32_t reserved;
     uint64_t call;           /* its launch counter (stamps hold call + 1)           */
     double c_gm_base, curv_base, rms_alpha;
+    double inv_num_data;     /* 1/N (BNNP_F_HYPER)                                   */
 } BnnpEpilogue;
 
 typedef struct BnnpLaunch {
@@ -156,7 +192,8 @@ typedef struct BnnpLaunch {
     float* prev_g;
     float* prev_m;
     const float* replay_noise; /* flat [total], BNNP_NOISE_REPLAY                   */
-    const BnnpSegment* segs;   /* [nseg]                                            */
+    BnnpSegment* segs;         /* [nseg]; only the epilogue of a BNNP_F_HYPER launch
+                                  writes it (prior_scale of linked segments)        */
     const int32_t* chunk_seg;  /* [all chunks]: segment of every chunk              */
     const int32_t* chunk_ids;  /* null: process chunks 0..nchunks-1; else [nchunks]
                                   chunk indices, whole segments only (used to skip

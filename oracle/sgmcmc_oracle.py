@@ -40,6 +40,11 @@ F32 = np.float32
 PRIOR_NONE, PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T = 0, 1, 2, 3
 # the other elementwise priors with constant hyper-parameters
 PRIOR_CAUCHY, PRIOR_GENNORM, PRIOR_LOGNORMAL, PRIOR_UNIFORM, PRIOR_IMPROPER, PRIOR_DOUBLE_GAMMA = 4, 5, 6, 7, 8, 9
+# SURVEY 8f/N4, second half: scalar hyper-parameters with their own prior (prior/hierarchical.py,
+# prior/empirical_bayes.py).  A hyper segment has one element u; its kind says how the scale of the
+# linked weight segment follows from u and which density the scale has.
+PRIOR_HYPER_GAMMA, PRIOR_HYPER_UNIFORM, PRIOR_HYPER_HALFCAUCHY, PRIOR_HYPER_IMPROPER = 10, 11, 12, 13
+HYPER_KINDS = (PRIOR_HYPER_GAMMA, PRIOR_HYPER_UNIFORM, PRIOR_HYPER_HALFCAUCHY, PRIOR_HYPER_IMPROPER)
 PHASE_INITIAL, PHASE_MID, PHASE_FINAL = 0, 1, 2
 
 
@@ -195,6 +200,64 @@ def prior_grad_log_prob(kind: int, p, loc: float, scale: float, df: float = 3.0)
 
 
 # --------------------------------------------------------------------------
+# Hierarchical priors: scale = f(u), u a sampled scalar with a hyper-prior.
+#   Gamma(concentration=a, rate=b) on s = softplus(u)      prior/transformed.py:50-63, hierarchical.py:17-22
+#   Uniform(low=a, high=a+b)       on s = a + b Phi(u)     prior/transformed.py:12-47, hierarchical.py:25-30
+#   HalfCauchy(scale=a) on s = softplus(u) * b             prior/transformed.py:66-80, hierarchical.py:85-90
+#   PositiveImproper: s = softplus(u), log density 0       prior/loc_scale.py:100-103, empirical_bayes.py:24-29
+# Scalars are float64 here (the reference's are fp32 0-dim tensors).
+# --------------------------------------------------------------------------
+def _softplus(u: float) -> float:
+    return u if u > 20.0 else math.log1p(math.exp(u))      # torch.nn.functional.softplus, threshold 20
+
+
+def _sigmoid(u: float) -> float:
+    return 1.0 / (1.0 + math.exp(-u))
+
+
+def hyper_scale(kind: int, u: float, a: float, b: float):
+    "(s, ds/du) of a hyper segment"
+    u = float(u)
+    if kind in (PRIOR_HYPER_GAMMA, PRIOR_HYPER_IMPROPER):
+        return _softplus(u), (1.0 if u > 20.0 else _sigmoid(u))
+    if kind == PRIOR_HYPER_HALFCAUCHY:
+        return _softplus(u) * b, (1.0 if u > 20.0 else _sigmoid(u)) * b
+    if kind == PRIOR_HYPER_UNIFORM:
+        cdf = 0.5 * math.erfc(-u / math.sqrt(2.0))
+        pdf = math.exp(-0.5 * u * u) / math.sqrt(2.0 * math.pi)
+        return a + b * cdf, b * pdf
+    raise ValueError(kind)
+
+
+def hyper_log_prob(kind: int, u: float, a: float, b: float):
+    "(log density of the scale, d/du of it) -- what scale_prior.log_prob() and autograd give"
+    s, ds = hyper_scale(kind, u, a, b)
+    if kind == PRIOR_HYPER_GAMMA:          # td.Gamma(a, b).log_prob(s)
+        return a * math.log(b) + (a - 1.0) * math.log(s) - b * s - math.lgamma(a), ((a - 1.0) / s - b) * ds
+    if kind == PRIOR_HYPER_UNIFORM:        # -log(high - low), prior/transformed.py:32-45
+        return -math.log(b), 0.0
+    if kind == PRIOR_HYPER_HALFCAUCHY:     # td.HalfCauchy(a).log_prob(s)
+        r = s / a
+        return math.log(2.0 / math.pi) - math.log(a) - math.log1p(r * r), -(2.0 * r / a) / (1.0 + r * r) * ds
+    if kind == PRIOR_HYPER_IMPROPER:
+        return 0.0, 0.0
+    raise ValueError(kind)
+
+
+def prior_dlog_prob_dscale(kind: int, p, loc: float, scale: float, df: float = 3.0) -> float:
+    "sum_i d log p(w_i | loc, s) / ds for the kinds a hyper-parameter may drive"
+    d = np.asarray(p, dtype=np.float64) - float(loc)
+    s, n = float(scale), d.size
+    if kind == PRIOR_NORMAL:
+        return float(np.sum(d * d)) / s ** 3 - n / s
+    if kind == PRIOR_LAPLACE:
+        return float(np.sum(np.abs(d))) / s ** 2 - n / s
+    if kind == PRIOR_STUDENT_T:
+        return (df + 1.0) * float(np.sum(d * d / (df * s * s + d * d))) / s - n / s
+    raise ValueError(f"prior kind {kind} cannot have a sampled scale")
+
+
+# --------------------------------------------------------------------------
 # Chain state
 # --------------------------------------------------------------------------
 @dataclass
@@ -216,6 +279,9 @@ class Segment:
     prior_loc: float = 0.0
     prior_scale: float = 1.0
     prior_df: float = 3.0
+    # hierarchical priors: a weight segment names its hyper segment, a hyper segment (one element,
+    # prior_kind in HYPER_KINDS, hyper-parameters a = prior_loc, b = prior_scale) its weight segment
+    link: int = -1
 
 
 @dataclass
@@ -289,20 +355,54 @@ def fuse_prior_into_grad(chain: Chain, grad_max: Optional[float] = None) -> None
     Restates models/base.py:72-77 (potential = loss - log_prior/N), the backward
     at inference.py:218 and the clamp at inference.py:219-220."""
     n = F32(chain.group.num_data)
+    refresh_hyper_scales(chain)
     for seg in chain.segs:
         if seg.prior_kind == PRIOR_NONE:
             continue
-        dl = prior_grad_log_prob(seg.prior_kind, seg.p, seg.prior_loc,
-                                 seg.prior_scale, seg.prior_df)
+        if seg.prior_kind in HYPER_KINDS:
+            # d/du [ sum_i log p(w_i | s(u)) + log p_hyper(s(u)) ] through autograd in the reference
+            w = chain.segs[seg.link]
+            _, ds = hyper_scale(seg.prior_kind, seg.p[0], seg.prior_loc, seg.prior_scale)
+            _, dlp = hyper_log_prob(seg.prior_kind, seg.p[0], seg.prior_loc, seg.prior_scale)
+            dl = np.array([prior_dlog_prob_dscale(w.prior_kind, w.p, w.prior_loc, w.prior_scale, w.prior_df) * ds
+                           + dlp], dtype=F32)
+        else:
+            dl = prior_grad_log_prob(seg.prior_kind, seg.p, seg.prior_loc,
+                                     seg.prior_scale, seg.prior_df)
         seg.g = (seg.g - dl / n).astype(F32)
         if grad_max is not None:
             np.clip(seg.g, -F32(grad_max), F32(grad_max), out=seg.g)
 
 
+def refresh_hyper_scales(chain: Chain) -> None:
+    "prior_scale of every weight segment that has a hyper segment, from the current u"
+    for seg in chain.segs:
+        if seg.prior_kind in HYPER_KINDS:
+            s, _ = hyper_scale(seg.prior_kind, seg.p[0], seg.prior_loc, seg.prior_scale)
+            chain.segs[seg.link].prior_scale = float(F32(s))
+
+
+def link_hyper(chain: Chain, weight: int, hyper: int, kind: int, a: float, b: float) -> None:
+    "declare segment `hyper` (one element) the scale hyper-parameter of segment `weight`"
+    h, w = chain.segs[hyper], chain.segs[weight]
+    assert h.p.size == 1 and kind in HYPER_KINDS
+    assert w.prior_kind in (PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T)
+    h.prior_kind, h.prior_loc, h.prior_scale, h.link = kind, float(a), float(b), weight
+    w.link = hyper
+    refresh_hyper_scales(chain)
+
+
 def log_prior(chain: Chain) -> float:
-    """models/base.py:25-30 restricted to the fused kinds."""
-    return sum(prior_log_prob(s.prior_kind, s.p, s.prior_loc, s.prior_scale, s.prior_df)
-               for s in chain.segs)
+    """models/base.py:25-30 restricted to the fused kinds (hyper segments contribute the
+    log density of their scale)."""
+    refresh_hyper_scales(chain)
+    total = 0.0
+    for s in chain.segs:
+        if s.prior_kind in HYPER_KINDS:
+            total += hyper_log_prob(s.prior_kind, s.p[0], s.prior_loc, s.prior_scale)[0]
+        else:
+            total += prior_log_prob(s.prior_kind, s.p, s.prior_loc, s.prior_scale, s.prior_df)
+    return total
 
 
 def _rmsprop(seg: Segment, alpha: float) -> None:

@@ -445,6 +445,53 @@ def golden_priors():
     print("priors:", [m["name"] for m in meta])
 
 
+def golden_hier_priors():
+    """SURVEY 8f N4, second half: priors whose scale is itself a sampled scalar with its
+    own prior (prior/hierarchical.py, prior/empirical_bayes.py).  For each class: the
+    weights p, the unconstrained hyper-parameter u (= scale_prior.p), the total
+    log-density  Prior.log_prob() + scale_prior.log_prob()  -- both are summed by
+    AbstractModel.log_prior (models/base.py:25-30, prior/base.py:79-81) -- and its
+    autograd gradients w.r.t. p and u, from the unmodified reference classes."""
+    from bnn_priors import prior as ref_prior
+    torch.manual_seed(2024)
+    H_GAMMA, H_UNIFORM, H_HALFCAUCHY, H_IMPROPER = 10, 11, 12, 13
+    cases = [
+        # name, class, ctor kwargs, weight kind, (hyper kind, a, b), u values tried
+        ("normal_gamma", ref_prior.NormalGamma, dict(loc=0.0, scale=0.8, rate=1.5), 1, (H_GAMMA, 0.8, 1.5)),
+        ("normal_uniform", ref_prior.NormalUniform, dict(loc=0.3, scale=0.6), 1, (H_UNIFORM, 0.0, 1.2)),
+        ("horseshoe", ref_prior.Horseshoe, dict(loc=0.0, scale=0.5, hyperscale=2.0), 1, (H_HALFCAUCHY, 2.0, 0.5)),
+        ("laplace_gamma", ref_prior.LaplaceGamma, dict(loc=-0.2, scale=1.3, rate=0.7), 2, (H_GAMMA, 1.3, 0.7)),
+        ("laplace_uniform", ref_prior.LaplaceUniform, dict(loc=0.0, scale=0.4), 2, (H_UNIFORM, 0.0, 0.8)),
+        ("studentt_gamma", ref_prior.StudentTGamma, dict(loc=0.0, scale=0.9, rate=1.0, df=2), 3, (H_GAMMA, 0.9, 1.0)),
+        ("studentt_uniform", ref_prior.StudentTUniform, dict(loc=0.1, scale=0.7, df=5), 3, (H_UNIFORM, 0.0, 1.4)),
+        ("normal_empirical", ref_prior.NormalEmpirical, dict(loc=0.0, scale=0.3), 1, (H_IMPROPER, 0.0, 1.0)),
+        ("laplace_empirical", ref_prior.LaplaceEmpirical, dict(loc=0.5, scale=1.1), 2, (H_IMPROPER, 0.0, 1.0)),
+    ]
+    out, meta = {}, []
+    for name, cls, kw, wkind, (hkind, ha, hb) in cases:
+        for j, du in enumerate((0.0, 0.9, -1.3)):
+            pm = cls(torch.Size([513]), **kw)
+            sp = pm.scale                                   # the hyper-prior module (a Prior with shape [])
+            assert isinstance(sp, ref_prior.Prior) and sp.p.numel() == 1
+            with torch.no_grad():
+                sp.p.add_(du)
+                s_now = float(sp())
+                pm.p.copy_(torch.randn(513) * 2 * s_now + kw["loc"])
+                pm.p[1] = kw["loc"] + 30 * s_now
+            lp = pm.log_prob() + sp.log_prob()
+            g_p, g_u = torch.autograd.grad(lp, [pm.p, sp.p])
+            tag = f"{name}_{j}"
+            out[tag + "_p"] = pm.p.detach().numpy().copy()
+            out[tag + "_grad_p"] = g_p.numpy().copy()
+            meta.append(dict(name=tag, kind=wkind, loc=kw["loc"], df=float(kw.get("df", 3.0)), hyper_kind=hkind,
+                             hyper_a=ha, hyper_b=hb, u=float(sp.p), scale=s_now, log_prob=float(lp),
+                             log_prob_weights=float(pm.log_prob()), log_prob_hyper=float(sp.log_prob()),
+                             grad_u=float(g_u)))
+    np.savez_compressed(os.path.join(HERE, "hier_priors.npz"),
+                        meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **out)
+    print("hier priors:", [(m["name"], round(m["scale"], 4), round(m["grad_u"], 3)) for m in meta])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     if os.environ.get("ONLY"): globals()[os.environ["ONLY"]](); sys.exit(0)
@@ -454,3 +501,4 @@ if __name__ == "__main__":
     golden_hmc()
     golden_runner()
     golden_priors()
+    golden_hier_priors()

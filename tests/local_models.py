@@ -20,14 +20,21 @@ class Prior(nn.Module):
         super().__init__()
         self.kwargs_keys = list(kwargs)
         for k, v in kwargs.items():
-            if isinstance(v, nn.Parameter):
+            if isinstance(v, nn.Module):          # a hyper-prior: the value is v() (prior/base.py:11-14,37-38)
+                self.add_module(k, v)
+            elif isinstance(v, nn.Parameter):
                 self.register_parameter(k, v)
             else:
                 self.register_buffer(k, torch.as_tensor(v, dtype=torch.float32))
-        self.p = nn.Parameter(self._dist_obj().sample(torch.Size(shape)))
+        with torch.no_grad():
+            self.p = nn.Parameter(self._sample_value(torch.Size(shape)))
+
+    def _sample_value(self, shape):
+        return self._dist_obj().sample(shape)
 
     def _dist_obj(self):
-        return self._dist(**{k: getattr(self, k) for k in self.kwargs_keys})
+        vals = {k: getattr(self, k) for k in self.kwargs_keys}
+        return self._dist(**{k: (v() if isinstance(v, nn.Module) else v) for k, v in vals.items()})
 
     def log_prob(self):
         return self._dist_obj().log_prob(self.p).sum()
@@ -138,6 +145,76 @@ class Improper(Normal):
 
     def log_prob(self):
         return 0. * self.p.sum()
+
+
+class PositiveImproper(Improper):
+    "prior/loc_scale.py:100-103: an improper prior on softplus(p)"
+
+    def forward(self):
+        return F.softplus(self.p)
+
+
+def _inv_softplus(x):
+    return x + torch.log(-torch.expm1(-x))
+
+
+class Gamma(Prior):
+    "prior/transformed.py:50-63: a Gamma density on softplus(p)"
+    _dist = td.Gamma
+
+    def __init__(self, shape, concentration, rate):
+        super().__init__(shape, concentration=concentration, rate=rate)
+
+    def _sample_value(self, shape):
+        return _inv_softplus(super()._sample_value(shape))
+
+    def forward(self):
+        return F.softplus(self.p)
+
+    def log_prob(self):
+        return self._dist_obj().log_prob(self()).sum()
+
+
+class HalfCauchy(Prior):
+    "prior/transformed.py:66-80"
+    _dist = td.HalfCauchy
+
+    def __init__(self, shape, scale=1., multiplier=1.):
+        super().__init__(shape, scale=scale)
+        self.multiplier = multiplier
+
+    def _sample_value(self, shape):
+        return _inv_softplus(super()._sample_value(shape))
+
+    def forward(self):
+        return F.softplus(self.p) * self.multiplier
+
+    def log_prob(self):
+        return self._dist_obj().log_prob(self()).sum()
+
+
+def hierarchical(base, hyper, **extra):
+    """The pattern of prior/hierarchical.py and prior/empirical_bayes.py: `base` (Normal /
+    Laplace / StudentT) whose scale is a scalar prior module, initialised so that the scale
+    starts at the nominal value.  hyper in {"gamma", "uniform", "horseshoe", "empirical"}."""
+    def make(shape, loc=0., scale=1.):
+        if hyper == "gamma":
+            sp = Gamma([], concentration=scale, rate=extra.get("rate", 1.))
+            init = _inv_softplus(torch.tensor(float(scale)))
+        elif hyper == "uniform":
+            sp = Uniform([], 0., scale * 2.)
+            init = torch.tensor(0.)
+        elif hyper == "horseshoe":
+            sp = HalfCauchy([], scale=extra.get("hyperscale", 1.), multiplier=scale)
+            init = _inv_softplus(torch.tensor(1.))
+        else:
+            sp = PositiveImproper([], 0., 1.)
+            init = _inv_softplus(torch.tensor(float(scale)))
+        with torch.no_grad():
+            sp.p.copy_(init)
+        kw = {"df": extra["df"]} if "df" in extra else {}
+        return base(shape, loc, sp, **kw)
+    return make
 
 
 class LearnedScaleNormal(Prior):

@@ -98,10 +98,24 @@ def test_python_constants_match_header():
 
 
 def test_struct_layouts_match_header():
-    # BnnpSegment: 3 x 8 + 3 x 4 + 3 x 4 = 48 bytes, natural alignment
-    assert N.SEGMENT_DTYPE.itemsize == 48
+    # BnnpSegment: 3 x 8 + 3 x 4 + 5 x 4 = 56 bytes, natural alignment
+    assert N.SEGMENT_DTYPE.itemsize == 56
     assert [N.SEGMENT_DTYPE.fields[k][1] for k in ("off", "numel", "precond", "prior_loc", "prior_kind",
-                                                   "first_chunk", "num_chunks")] == [0, 8, 16, 24, 36, 40, 44]
+                                                   "first_chunk", "num_chunks", "link")] == [0, 8, 16, 24, 36, 40, 44, 48]
+    seg = re.search(r"typedef struct BnnpSegment \{(.*?)\} BnnpSegment;", HEADER, flags=re.S).group(1)
+    seg = re.sub(r"/\*.*?\*/", "", seg, flags=re.S)
+    seg_names = []
+    for decl in seg.split(";"):
+        decl = re.sub(r"^[A-Za-z_0-9]+\s*", "", decl.strip(), count=1)
+        seg_names += [x.strip() for x in decl.split(",") if x.strip()]
+    assert seg_names == list(N.SEGMENT_DTYPE.names)
+    epi = re.search(r"typedef struct BnnpEpilogue \{(.*?)\} BnnpEpilogue;", HEADER, flags=re.S).group(1)
+    epi = re.sub(r"/\*.*?\*/", "", epi, flags=re.S)
+    epi_names = []
+    for decl in epi.split(";"):
+        decl = re.sub(r"^[A-Za-z_0-9]+\s*", "", decl.strip(), count=1)
+        epi_names += [x.strip() for x in decl.split(",") if x.strip()]
+    assert epi_names == [f[0] for f in N.BnnpEpilogue._fields_]
     fields = re.search(r"typedef struct BnnpLaunch \{(.*?)\} BnnpLaunch;", HEADER, flags=re.S).group(1)
     fields = re.sub(r"/\*.*?\*/", "", fields, flags=re.S)
     names = []
@@ -145,8 +159,16 @@ def test_launch_validates_arguments_without_a_gpu(lib):
     a.nchunks = 1
     a.pending.valid, a.pending.parity, a.parity = 1, 0, 0
     assert lib.bnnp_launch(C.byref(a), None) == -1 and b"overwrite the partial records" in lib.bnnp_last_error()
-    a.pending.valid = 0
+    a.pending.valid, a.pending.parity, a.pending.flags = 1, 1, N.F_HYPER
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"bnnp_finalize first" in lib.bnnp_last_error()
+    a.pending.valid, a.pending.flags = 0, 0
     assert lib.bnnp_finalize(C.byref(a), None) == 0             # nothing pending: no-op, no CUDA call
+    a.P = 4096
+    a.op, a.flags = N.OP_SGLD, N.F_HYPER | N.F_READ_P | N.F_LOG_PRIOR
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"read-only pre-pass" in lib.bnnp_last_error()
+    a.op, a.flags = N.OP_REDUCE, N.F_HYPER | N.F_READ_P | N.F_LOG_PRIOR | N.F_WRITE_P
+    assert lib.bnnp_launch(C.byref(a), None) == -1 and b"read-only pre-pass" in lib.bnnp_last_error()
+    a.op, a.flags, a.P = 0, 0, None
     a.op = 9
     assert lib.bnnp_launch(C.byref(a), None) == -1 and b"bad op" in lib.bnnp_last_error()
     a.op, a.flags = N.OP_SGLD, N.F_READ_P

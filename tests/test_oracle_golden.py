@@ -124,3 +124,25 @@ def test_eval_oracle_reproduces_reference_results(tag, kind):
     got1 = EO.evaluate(z[f"{tag}.acc_data"][-1:], z[f"{tag}.lps"][-1:], z[f"{tag}.y"], kind)
     for k in ("lp_ensemble", "lp_last", "acc_ensemble", "acc_last"):
         assert math.isclose(got1[k], want1[k], rel_tol=1e-7, abs_tol=1e-7), (k, got1[k], want1[k])
+
+
+# ---- hierarchical priors (second half) against the reference's autograd
+def _hier_cases():
+    z = np.load(os.path.join(GOLDEN_DIR, "hier_priors.npz"))
+    return z, json.loads(bytes(z["meta"]).decode())
+
+
+@pytest.mark.parametrize("case", _hier_cases()[1], ids=[m["name"] for m in _hier_cases()[1]])
+def test_oracle_hierarchical_prior_matches_reference_autograd(case):
+    z, _ = _hier_cases()
+    p, g_ref = z[case["name"] + "_p"], z[case["name"] + "_grad_p"]
+    s, _ = O.hyper_scale(case["hyper_kind"], case["u"], case["hyper_a"], case["hyper_b"])
+    assert math.isclose(s, case["scale"], rel_tol=2e-6)
+    ch = O.Chain([p, np.array([case["u"]], np.float32)], O.Group(lr=1.0, num_data=1.0))
+    ch.segs[0].prior_kind, ch.segs[0].prior_loc, ch.segs[0].prior_df = case["kind"], case["loc"], case["df"]
+    O.link_hyper(ch, 0, 1, case["hyper_kind"], case["hyper_a"], case["hyper_b"])
+    assert math.isclose(O.log_prior(ch), case["log_prob"], rel_tol=5e-6, abs_tol=1e-4)
+    O.fuse_prior_into_grad(ch)            # zero likelihood gradient, N = 1: g = -dlogp
+    got_p, got_u = -ch.segs[0].g, -float(ch.segs[1].g[0])
+    assert np.allclose(got_p, g_ref, rtol=2e-5, atol=1e-6 * np.abs(g_ref).max())
+    assert math.isclose(got_u, case["grad_u"], rel_tol=2e-5, abs_tol=1e-4), (got_u, case["grad_u"])
