@@ -48,11 +48,6 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 
 // exp_utils.py:279-297 for one batch of one sample
 __global__ void __launch_bounds__(EV_THREADS) eval_batch_kernel(const BnnpEvalState st, const float* __restrict__ acc,

@@ -193,6 +193,15 @@ __device__ __forceinline__ void hyper_scale(const BnnpSegment& h, double u, doub
     ds = sg * mult;
 }
 
+// the same scale in float32 (what the reference's fp32 softplus / Normal.cdf give): used by every
+// thread of a pre-pass CTA, where the float64 version above would dominate the launch
+__device__ __forceinline__ float hyper_scale_f32(const BnnpSegment& h, float u) {
+    if (h.prior_kind == BNNP_PRIOR_HYPER_UNIFORM)
+        return fmaf(h.prior_scale, 0.5f * erfcf(-u * 0.70710678118654752f), h.prior_loc);
+    const float sp = u > 20.0f ? u : log1pf(expf(u));
+    return h.prior_kind == BNNP_PRIOR_HYPER_HALFCAUCHY ? sp * h.prior_scale : sp;
+}
+
 template <int FORM>
 __device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double inv_n, float hyper_term) {
     PriorConst pc;
@@ -356,10 +365,6 @@ __device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c,
             acc[R_PG] = fmaf(p0, gj, acc[R_PG]);
         }
         const float pn = fmaf(c.cpM, t, p0);      // stored only with BNNP_F_WRITE_P
-        if (PRIOR && SUMS == SUMS_ALL && (KIND == F_NORMAL || KIND == F_LAPLACE || KIND == F_STUDENT_T)) {
-            // pre-pass of the hierarchical priors: g and m are not read, the slot is free
-            if ((flags & BNNP_F_HYPER) && j < valid) acc[R_GM_OLD] += scale_stat_term<KIND>(pc, p0);
-        }
         if (PRIOR && KIND != F_NONE && KIND != F_CONST) {
             if ((flags & BNNP_F_LOG_PRIOR) && j < valid)
                 acc[R_LOGP] += log_prior_term<KIND>(pc, (flags & BNNP_F_WRITE_P) ? pn : p0);
@@ -476,6 +481,22 @@ __device__ void segment_epilogue(const BnnpEpilogue& E, double* seg_state, const
     st[BNNP_S_LAUNCHES] += 1.0;
 }
 
+// One warp: the sum over `num_chunks` partial records of one reduction slot (stride BNNP_NRED
+// doubles).  Eight independent running sums per lane keep eight L2 loads in flight; they are
+// combined in a fixed order, so the result does not depend on timing.
+__device__ __forceinline__ double fold_records(const double* base, int num_chunks, int lane) {
+    double s[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    for (int ch = lane; ch < num_chunks; ch += 32 * 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch + 32 * j;
+            if (c < num_chunks) s[j] += ld_cg_f64(base + (int64_t)c * BNNP_NRED);
+        }
+    }
+    const double t = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    return warp_sum_f64(t);
+}
+
 // CTA-wide: fold the partial records launch `L.pending` left for segment `seg` (one warp
 // per sum, lanes over the chunks, fp64, fixed order) and apply its epilogue.  A segment
 // the pending launch skipped carries an older stamp and is left alone.
@@ -485,19 +506,7 @@ __device__ void apply_pending(const BnnpLaunch& L, const BnnpSegment& sd, int se
     const int64_t rec0 = (int64_t)E.parity * L.nchunks_total + sd.first_chunk;
     if (L.stamps[rec0] != E.call + 1) return;     // uniform over the CTA
     for (int k = warp; k < BNNP_NRED; k += NWARPS) {
-        const double* base = L.partials + rec0 * BNNP_NRED + k;
-        // eight independent running sums per lane keep eight L2 loads in flight; they are
-        // combined in a fixed order, so the result does not depend on timing
-        double s[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
-        for (int ch = lane; ch < sd.num_chunks; ch += 32 * 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = ch + 32 * j;
-                if (c < sd.num_chunks) s[j] += ld_cg_f64(base + (int64_t)c * BNNP_NRED);
-            }
-        }
-        double t = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-        t = warp_sum_f64(t);
+        const double t = fold_records(L.partials + rec0 * BNNP_NRED + k, sd.num_chunks, lane);
         if (lane == 0) s_sum[k] = t;
     }
     if ((E.flags & BNNP_F_HYPER) && is_hyper_kind(sd.prior_kind) && sd.link >= 0 && sd.link < L.nseg && warp == 0) {
@@ -505,9 +514,7 @@ __device__ void apply_pending(const BnnpLaunch& L, const BnnpSegment& sd, int se
         // here, so that no CTA depends on another CTA's epilogue
         const BnnpSegment w = L.segs[sd.link];
         const double* base = L.partials + ((int64_t)E.parity * L.nchunks_total + w.first_chunk) * BNNP_NRED + R_GM_OLD;
-        double t = 0.0;
-        for (int ch = lane; ch < w.num_chunks; ch += 32) t += ld_cg_f64(base + (int64_t)ch * BNNP_NRED);
-        t = warp_sum_f64(t);
+        const double t = fold_records(base, w.num_chunks, lane);
         if (lane == 0) s_sum[BNNP_NRED] = t;
     }
     __syncthreads();
@@ -579,7 +586,7 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     const int tid = threadIdx.x;
     const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[blockIdx.x] : (int)blockIdx.x;
     const int seg = L.chunk_seg[chunk];
-    BnnpSegment sd = L.segs[seg];
+    const BnnpSegment sd = L.segs[seg];
     // the previous launch's bookkeeping: segment j is handled by CTA j, i.e. by the CTAs that
     // start first, so the few microseconds it takes are absorbed at the front of the launch
     if (L.pending.valid && (int)blockIdx.x < L.nseg) apply_pending(L, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
@@ -622,12 +629,6 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
             // -(1/N) d log p / du, left by the epilogue of the BNNP_F_HYPER pre-pass (finalised before
             // this launch started: bnnp_launch refuses a pending BNNP_F_HYPER epilogue)
             hyper_term = (float)L.seg_state[(int64_t)seg * BNNP_STATE_STRIDE + BNNP_S_HYPER];
-        } else if ((flags & BNNP_F_HYPER) && sd.link >= 0 && sd.link < L.nseg && may_have_hyper_scale(sd.prior_kind)) {
-            // pre-pass: the scale is what the hyper-parameter now in P says (nobody writes P in this launch)
-            const BnnpSegment h = L.segs[sd.link];
-            double s, ds;
-            hyper_scale(h, (double)L.P[h.off], s, ds);
-            sd.prior_scale = (float)s;
         }
 #define BNNP_FORM_CASE(F)                                                                                      \
     case F:                                                                                                    \
@@ -674,6 +675,96 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
         L.partials[((int64_t)L.parity * L.nchunks_total + chunk) * BNNP_NRED + tid] = s;
     }
     if (tid == 0) L.stamps[(int64_t)L.parity * L.nchunks_total + chunk] = L.call + 1;   // "this launch wrote it"
+}
+
+// ---------------------------------------------------------------------------------
+// The pre-pass of the hierarchical priors (BNNP_F_HYPER): reads P only and reduces, per
+// chunk, sum log p(theta | s(u)) (slot R_LOGP) and the statistic of d log p / d scale (slot
+// R_GM_OLD), with the scale of a linked segment taken from the hyper-parameter u now in P.
+// Same chunking, partial records and deferred epilogue as the step kernel, but 16 KB per CTA
+// instead of 80 KB: what bounds it is the per-CTA latency chain (chunk -> segment -> hyper
+// segment -> u), so it is kept lean enough for BNNP_PREPASS_CTAS resident CTAs per SM.
+// ---------------------------------------------------------------------------------
+#ifndef BNNP_PREPASS_CTAS
+#define BNNP_PREPASS_CTAS 8
+#endif
+
+template <int FORM>
+__device__ __forceinline__ void prepass_quads(const PriorConst& pc, const ChunkCtx& cx, const F4 (&p)[UNROLL],
+                                              float& logp, float& stat) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int e = (u * THREADS + cx.tid) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (e + j < cx.rem) {
+                logp += log_prior_term<FORM>(pc, p[u].f[j]);
+                stat += scale_stat_term<FORM>(pc, p[u].f[j]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, BNNP_PREPASS_CTAS) bnnp_prepass_kernel(const __grid_constant__ StepParams S) {
+    __shared__ double s_red[NWARPS][BNNP_NRED];
+    const BnnpLaunch& L = S.L;
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.x;
+    const int seg = L.chunk_seg[chunk];
+    BnnpSegment sd = L.segs[seg];
+    if (L.pending.valid && (int)blockIdx.x < L.nseg) apply_pending(L, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
+    const int64_t cbase = (int64_t)(chunk - sd.first_chunk) * CHUNK;
+    const int64_t left = sd.numel - cbase;
+    ChunkCtx cx;
+    cx.rem = left < (int64_t)CHUNK ? (int)left : CHUNK;
+    cx.fbase = sd.off + cbase;
+    cx.tid = tid;
+
+    F4 p[UNROLL];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int e = (u * THREADS + tid) * 4;
+        p[u].v = e < cx.rem ? ld_f4(L.P + cx.fbase + e) : zero4;
+    }
+    if (sd.link >= 0 && sd.link < L.nseg && may_have_hyper_scale(sd.prior_kind)) {
+        const BnnpSegment h = L.segs[sd.link];
+        sd.prior_scale = hyper_scale_f32(h, L.P[h.off]);
+    }
+    float logp = 0.0f, stat = 0.0f;
+    switch (prior_form(sd.prior_kind)) {
+#define BNNP_PRE_CASE(F) \
+    case F: prepass_quads<F>(make_prior<F>(sd, L.inv_num_data, 0.0f), cx, p, logp, stat); break;
+        BNNP_PRE_CASE(F_NORMAL)
+        BNNP_PRE_CASE(F_LOGNORMAL)
+        BNNP_PRE_CASE(F_LAPLACE)
+        BNNP_PRE_CASE(F_STUDENT_T)
+        BNNP_PRE_CASE(F_GENNORM)
+        BNNP_PRE_CASE(F_DOUBLE_GAMMA)
+#undef BNNP_PRE_CASE
+        default: break;     // no prior, constant densities, hyper segments: the epilogue adds their constants
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        logp += __shfl_xor_sync(0xffffffffu, logp, o);
+        stat += __shfl_xor_sync(0xffffffffu, stat, o);
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) {
+        s_red[warp][0] = (double)logp;
+        s_red[warp][1] = (double)stat;
+    }
+    __syncthreads();
+    if (tid < BNNP_NRED) {
+        double s = 0.0;
+        if (tid == R_LOGP || tid == R_GM_OLD) {
+            const int k = tid == R_LOGP ? 0 : 1;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) s += s_red[w][k];
+        }
+        L.partials[((int64_t)L.parity * L.nchunks_total + chunk) * BNNP_NRED + tid] = s;
+    }
+    if (tid == 0) L.stamps[(int64_t)L.parity * L.nchunks_total + chunk] = L.call + 1;
 }
 
 // bnnp_finalize: the pending epilogue of every segment, nothing else
@@ -839,13 +930,14 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
         return fail(BNNP_E_ARG, "bnnp_launch: the epilogue of a BNNP_F_HYPER launch rewrites the segment table; "
                                 "bnnp_finalize first");
     if ((f & BNNP_F_HYPER) &&
-        (a->op != BNNP_OP_REDUCE || (f & (BNNP_F_WRITE_P | BNNP_F_PRIOR_GRAD)) || !(f & BNNP_F_LOG_PRIOR) ||
-         !(f & BNNP_F_READ_P) || a->chunk_ids != nullptr))
+        (a->op != BNNP_OP_REDUCE || !(f & BNNP_F_LOG_PRIOR) || !(f & BNNP_F_READ_P) || a->chunk_ids != nullptr ||
+         (f & ~(uint32_t)(BNNP_F_HYPER | BNNP_F_LOG_PRIOR | BNNP_F_READ_P))))
         return fail(BNNP_E_ARG, "bnnp_launch: BNNP_F_HYPER is the read-only pre-pass: BNNP_OP_REDUCE over all "
-                                "chunks with READ_P | LOG_PRIOR, no WRITE_P / PRIOR_GRAD");
+                                "chunks with exactly READ_P | LOG_PRIOR | HYPER");
     const bool prior = (f & (BNNP_F_LOG_PRIOR | BNNP_F_PRIOR_GRAD)) != 0;
     if (prior && !(f & BNNP_F_READ_P)) return fail(BNNP_E_ARG, "bnnp_launch: the prior needs READ_P");
-    StepKernel k = pick_kernel(a->noise, prior, (f & BNNP_F_NOISE_FIRST) != 0, sums_needed(a->op, f));
+    StepKernel k = (f & BNNP_F_HYPER) ? bnnp_prepass_kernel
+                                      : pick_kernel(a->noise, prior, (f & BNNP_F_NOISE_FIRST) != 0, sums_needed(a->op, f));
     if (k == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: bad noise kind");
     StepParams sp;
     sp.L = *a;

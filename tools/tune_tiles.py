@@ -35,6 +35,39 @@ for name, smp, fused, call in cases:
     out[name] = [round(ms[0] * 1e3, 2), round(ms[2] * 1e3, 2)]      # min, median of 5
     del opt, params, fg
     torch.cuda.empty_cache()
+if not only or "verlet_hier" in only.split(","):
+    # hierarchical priors: every weight tensor with a prior gets a sampled scale
+    # (NormalGamma); a step = read-only pre-pass over P + its epilogue + the step launch
+    from bnn_priors_b200 import _native as N, mcmc
+    tensors = bench.load_tensors()
+    g = torch.Generator(device=dev).manual_seed(0)
+    params, links = [], []
+    for t in tensors:
+        params.append(torch.nn.Parameter(torch.randn(tuple(t["shape"]), device=dev, generator=g) * (t["scale"] if t["kind"] else 1.0)))
+        if t["kind"] and len(t["shape"]) > 1:
+            links.append((len(params) - 1, len(params), t))
+            params.append(torch.nn.Parameter(torch.tensor(0.1, device=dev)))
+    opt = mcmc.VerletSGLD(params, **bench.HP, seed=0)
+    (fg,) = opt.flat_groups
+    for w, h, t in links:
+        fg.set_prior(w, N.PRIOR_NORMAL, 0.0, t["scale"], 3.0)
+        fg.set_hyper_link(w, h, N.PRIOR_HYPER_GAMMA, 1.0, 1.0)
+    fg.prior_fused = True
+    for p, v in zip(params, fg.g_views):
+        p.grad = v
+        v.normal_(0.0, 1e-3, generator=g)
+    opt.sample_momentum()
+    step = lambda: opt.step(calc_metrics=False)  # noqa: E731
+    for _ in range(50):
+        step()
+    ms = sorted(bench.timed_gpu(step, K, dev, False) / K for _ in range(5))
+    out["verlet_hier"] = [round(ms[0] * 1e3, 2), round(ms[2] * 1e3, 2)]
+    out["verlet_hier_links"] = len(links)
+    pre = lambda: fg.hyper_prepass(1.0 / bench.HP["num_data"])  # noqa: E731
+    ms = sorted(bench.timed_gpu(pre, K, dev, False) / K for _ in range(5))
+    out["hier_prepass_plus_epilogue"] = [round(ms[0] * 1e3, 2), round(ms[2] * 1e3, 2)]
+    del opt, params, fg
+    torch.cuda.empty_cache()
 if not only or "probe" in only.split(","):
     # ceiling of the access pattern: read p, g, m / write p, m and nothing else
     from bnn_priors_b200 import _native as N
