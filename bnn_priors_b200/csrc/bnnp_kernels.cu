@@ -305,6 +305,45 @@ union F4 {
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st_f4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 
+// L2 eviction-priority hints (createpolicy encodings; PTX ld/st .L2::cache_hint).  Consecutive
+// launches walk the chain in opposite directions (BNNP_F_REVERSE), so what a launch leaves in the
+// 126 MB L2 is what the next one reads first.  A parameter / momentum line kept there saves a DRAM
+// read AND a write-back, so P and M are accessed evict-last; the snapshot stores (read again only
+// after a rejection) are evict-first.  Measured (profiles/r01f_notes.md): serpentine order 79.1 ->
+// 69.7 us per SGLD step, + evict-last P/M 67.5 us; evict-first gradient loads made no difference.
+constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
+#ifndef BNNP_G_POLICY
+#define BNNP_G_POLICY 0     // 0: plain loads, 1: evict-first
+#endif
+#ifndef BNNP_PM_POLICY
+#define BNNP_PM_POLICY 2    // 0: plain, 1: evict-last stores, 2: evict-last loads and stores
+#endif
+
+__device__ __forceinline__ float4 ld_f4_hint(const float* p, uint64_t policy) {
+    float4 v;
+    asm("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void st_f4_hint(float* p, const float4& v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 :
+                 : "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ float4 ld_grad(const float* p) {
+    return BNNP_G_POLICY == 1 ? ld_f4_hint(p, POLICY_EVICT_FIRST) : ld_f4(p);
+}
+__device__ __forceinline__ float4 ld_state(const float* p) {
+    return BNNP_PM_POLICY == 2 ? ld_f4_hint(p, POLICY_EVICT_LAST) : ld_f4(p);
+}
+__device__ __forceinline__ void st_state(float* p, const float4& v) {
+    if (BNNP_PM_POLICY >= 1) st_f4_hint(p, v, POLICY_EVICT_LAST);
+    else st_f4(p, v);
+}
+
 __device__ __forceinline__ double ld_cg_f64(const double* p) {
     double v;
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -545,9 +584,9 @@ __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCt
         if (e >= cx.rem) continue;
         const int64_t fi = cx.fbase + e;
         if (flags & BNNP_F_SAVE_STATE) {   // verlet_sgld.py:72-83, the values BEFORE the update
-            st_f4(L.prev_p + fi, p[u].v);
-            st_f4(L.prev_g + fi, g[u].v);
-            if (L.prev_m != nullptr) st_f4(L.prev_m + fi, m[u].v);
+            st_f4_hint(L.prev_p + fi, p[u].v, POLICY_EVICT_FIRST);
+            st_f4_hint(L.prev_g + fi, g[u].v, POLICY_EVICT_FIRST);
+            if (L.prev_m != nullptr) st_f4_hint(L.prev_m + fi, m[u].v, POLICY_EVICT_FIRST);
         }
         if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)fi >> 2, L.call, keys, z[u].f);
         const int valid = cx.rem - e;
@@ -557,8 +596,8 @@ __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCt
                 if (j >= valid) p[u].f[j] = g[u].f[j] = m[u].f[j] = z[u].f[j] = 0.0f;
         }
         update_quad<NOISE, PRIOR, KIND, NOISE_FIRST, SUMS>(flags, c, pc, valid, p[u], g[u], m[u], z[u].f, acc);
-        if (flags & BNNP_F_WRITE_P) st_f4(L.P + fi, p[u].v);
-        if (flags & BNNP_F_WRITE_M) st_f4(L.M + fi, m[u].v);
+        if (flags & BNNP_F_WRITE_P) st_state(L.P + fi, p[u].v);
+        if (flags & BNNP_F_WRITE_M) st_state(L.M + fi, m[u].v);
     }
 }
 
@@ -584,7 +623,8 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     const PhiloxKeys& keys = S.keys;
 
     const int tid = threadIdx.x;
-    const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[blockIdx.x] : (int)blockIdx.x;
+    const int slot = (L.flags & BNNP_F_REVERSE) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[slot] : slot;
     const int seg = L.chunk_seg[chunk];
     const BnnpSegment sd = L.segs[seg];
     // the previous launch's bookkeeping: segment j is handled by CTA j, i.e. by the CTAs that
@@ -612,9 +652,9 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     for (int u = 0; u < UNROLL; ++u) {
         const int e = (u * THREADS + tid) * 4;
         const bool act = e < cx.rem;
-        p[u].v = (act && (flags & BNNP_F_READ_P)) ? ld_f4(L.P + cx.fbase + e) : zero4;
-        g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_f4(L.G + cx.fbase + e) : zero4;
-        m[u].v = (act && (flags & BNNP_F_READ_M)) ? ld_f4(L.M + cx.fbase + e) : zero4;
+        p[u].v = (act && (flags & BNNP_F_READ_P)) ? ld_state(L.P + cx.fbase + e) : zero4;
+        g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_grad(L.G + cx.fbase + e) : zero4;
+        m[u].v = (act && (flags & BNNP_F_READ_M)) ? ld_state(L.M + cx.fbase + e) : zero4;
         if (NOISE == BNNP_NOISE_REPLAY) z[u].v = act ? ld_f4(L.replay_noise + cx.fbase + e) : zero4;
         else z[u].v = zero4;
     }
@@ -709,7 +749,7 @@ __global__ void __launch_bounds__(THREADS, BNNP_PREPASS_CTAS) bnnp_prepass_kerne
     __shared__ double s_red[NWARPS][BNNP_NRED];
     const BnnpLaunch& L = S.L;
     const int tid = threadIdx.x;
-    const int chunk = blockIdx.x;
+    const int chunk = (L.flags & BNNP_F_REVERSE) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
     const int seg = L.chunk_seg[chunk];
     BnnpSegment sd = L.segs[seg];
     if (L.pending.valid && (int)blockIdx.x < L.nseg) apply_pending(L, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
@@ -931,7 +971,7 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
                                 "bnnp_finalize first");
     if ((f & BNNP_F_HYPER) &&
         (a->op != BNNP_OP_REDUCE || !(f & BNNP_F_LOG_PRIOR) || !(f & BNNP_F_READ_P) || a->chunk_ids != nullptr ||
-         (f & ~(uint32_t)(BNNP_F_HYPER | BNNP_F_LOG_PRIOR | BNNP_F_READ_P))))
+         (f & ~(uint32_t)(BNNP_F_HYPER | BNNP_F_LOG_PRIOR | BNNP_F_READ_P | BNNP_F_REVERSE))))
         return fail(BNNP_E_ARG, "bnnp_launch: BNNP_F_HYPER is the read-only pre-pass: BNNP_OP_REDUCE over all "
                                 "chunks with exactly READ_P | LOG_PRIOR | HYPER");
     const bool prior = (f & (BNNP_F_LOG_PRIOR | BNNP_F_PRIOR_GRAD)) != 0;

@@ -13,6 +13,7 @@ torch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -206,6 +207,7 @@ class FlatGroup:
 
         self._mom_published = False
         self._tables_set = False
+        self.serpentine = os.environ.get("BNNP_SERPENTINE", "1") != "0"
         self.seg_states = [SegState(self, i) for i in range(self.nseg)]
         self._sync_rows = list(zip(self.params, self.g_views, self.p_views, self._p_ptrs))
         self.args = N.BnnpLaunch()
@@ -434,6 +436,10 @@ class FlatGroup:
         segment) and leaves its own pending."""
         self._set_pending(a)
         a.parity, a.call = self._parity, self.call
+        if self.serpentine:
+            # alternate the chunk order from launch to launch: each launch starts on the lines the
+            # previous one left in L2 (include/bnnp.h: BNNP_F_REVERSE)
+            a.flags = (a.flags | N.F_REVERSE) if self._parity else (a.flags & ~N.F_REVERSE)
         if torch.cuda.current_device() != self._dev_index:
             with torch.cuda.device(self.device):
                 rc = self.lib.bnnp_launch(C.byref(a), self._stream())

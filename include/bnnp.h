@@ -115,6 +115,11 @@ enum {
                                        (HMC initial/final need m.m: hmc.py:50-53,32-33);
                                        otherwise a launch only reduces what its epilogue
                                        reads: g.g always, g.m and g.m' for VERLET       */
+    BNNP_F_REVERSE = 1u << 15,      /* CTA i processes chunk nchunks-1-i.  A chain larger than
+                                       L2 that alternates the direction from launch to launch
+                                       starts each launch on the lines the previous one
+                                       touched last, which are still in the 126 MB L2
+                                       (results do not depend on the order)               */
     BNNP_F_HYPER = 1u << 14         /* the hierarchical-prior pre-pass (BNNP_OP_REDUCE with
                                        READ_P | LOG_PRIOR, no writes to P): linked segments
                                        take their scale from the hyper-parameter u now in P,

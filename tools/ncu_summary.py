@@ -86,11 +86,37 @@ def summarise_launches(path):
             for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])]
 
 
+def summarise_dram(path, pattern="bnnp_step_kernel"):
+    """Per-launch DRAM bytes of consecutive launches profiled in ONE pass with
+    `--cache-control none` (no replay, no flush: the L2 state is the one the previous
+    launch left, as in the timed region of bench.py)."""
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ki, mi, ui, vi, ii = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Unit", "Metric Value", "ID"))
+    per = defaultdict(dict)
+    for r in rows[1:]:
+        if pattern in r[ki]:
+            v = to_float(r[vi])
+            if isinstance(v, float):
+                mult = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-3, "us": 1.0, "usecond": 1.0,
+                        "nsecond": 1e-3, "msecond": 1e3}.get(r[ui].lower(), 1)
+                per[r[ii]][r[mi]] = v * mult
+    ls = [d for d in per.values() if "dram__bytes_read.sum" in d and "dram__bytes_write.sum" in d]
+    n = len(ls)
+    return {"launches": n,
+            "dram_bytes_read_per_launch": sum(d["dram__bytes_read.sum"] for d in ls) / n,
+            "dram_bytes_write_per_launch": sum(d["dram__bytes_write.sum"] for d in ls) / n,
+            "dram_bytes_per_launch": sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in ls) / n,
+            "us_per_launch_under_ncu": sum(d.get("gpu__time_duration.sum", 0.0) for d in ls) / n,
+            "per_launch_mb": [round((d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]) / 1e6, 1) for d in ls]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tag", required=True)
     ap.add_argument("--rep")
     ap.add_argument("--launches")
+    ap.add_argument("--dram-csv", help="single-pass dram__bytes capture with --cache-control none")
     ap.add_argument("--note", default="")
     a = ap.parse_args()
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
@@ -110,6 +136,22 @@ def main():
             json.dump({k: v for k, v in summary.items() if k != "kernels"} | {"tag": a.tag}, f, indent=1)
         for k in mine[:1]:
             print(json.dumps({m: v["value"] for m, v in k.items() if isinstance(v, dict)}, indent=1))
+    if a.dram_csv:
+        d = summarise_dram(a.dram_csv)
+        d["note"] = ("steady state: consecutive launches, one ncu pass, --cache-control none (L2 as the previous launch "
+                     "left it). " + a.note)
+        with open(os.path.join(ROOT, "profiles", f"{a.tag}_ncu_dram_steady.json"), "w") as f:
+            json.dump(d, f, indent=1)
+        fixed = os.path.join(ROOT, "profiles", "ncu_step_kernel.json")
+        cur = json.load(open(fixed)) if os.path.exists(fixed) else {}
+        if "dram_bytes_per_launch" in cur and "dram_bytes_per_launch_cold" not in cur:
+            cur["dram_bytes_per_launch_cold"] = cur["dram_bytes_per_launch"]      # the --set full capture flushes caches
+        cur.update({"dram_bytes_per_launch": d["dram_bytes_per_launch"], "steady_tag": a.tag,
+                    "dram_bytes_read_per_launch": d["dram_bytes_read_per_launch"],
+                    "dram_bytes_write_per_launch": d["dram_bytes_write_per_launch"]})
+        with open(fixed, "w") as f:
+            json.dump(cur, f, indent=1)
+        print(json.dumps({k: v for k, v in d.items() if k != "note"}))
     if a.launches:
         ls = summarise_launches(a.launches)
         with open(os.path.join(ROOT, "profiles", f"{a.tag}_ncu_launches.json"), "w") as f:
