@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BNNP_LIB") or os.path.join(HERE, "_lib", "libbnnp.so")
 
 # ---- constants of include/bnnp.h (tests/test_abi.py checks them against the header)
-ABI_VERSION = 6
+ABI_VERSION = 7
 SEG_ALIGN = 32
 THREADS = 256
 UNROLL = 4
@@ -59,6 +59,11 @@ SEGMENT_DTYPE = np.dtype([
 assert SEGMENT_DTYPE.itemsize == 56
 
 
+# BnnpChunk
+CHUNK_DTYPE = np.dtype([("fbase", np.int64), ("rem", np.int32), ("seg", np.int32)], align=True)
+assert CHUNK_DTYPE.itemsize == 16
+
+
 class BnnpEpilogue(C.Structure):
     _fields_ = [
         ("valid", C.c_int32), ("op", C.c_int32), ("phase", C.c_int32), ("flags", C.c_uint32),
@@ -73,7 +78,7 @@ class BnnpLaunch(C.Structure):
         ("P", C.c_void_p), ("G", C.c_void_p), ("M", C.c_void_p),
         ("prev_p", C.c_void_p), ("prev_g", C.c_void_p), ("prev_m", C.c_void_p),
         ("replay_noise", C.c_void_p),
-        ("segs", C.c_void_p), ("chunk_seg", C.c_void_p), ("chunk_ids", C.c_void_p), ("seg_state", C.c_void_p),
+        ("segs", C.c_void_p), ("chunks", C.c_void_p), ("chunk_ids", C.c_void_p), ("seg_state", C.c_void_p),
         ("partials", C.c_void_p), ("stamps", C.c_void_p),
         ("nseg", C.c_int32), ("nchunks", C.c_int32), ("nchunks_total", C.c_int32), ("parity", C.c_int32),
         ("op", C.c_int32), ("phase", C.c_int32), ("noise", C.c_int32),
@@ -158,7 +163,7 @@ def check_eval(rc: int, what: str) -> None:
 
 def plan_layout(numels):
     """Host-side layout planner (bnnp_plan_layout).  Returns
-    (off[nseg], first_chunk[nseg], num_chunks[nseg], total_elems, chunk_seg[nchunks])."""
+    (off[nseg], first_chunk[nseg], num_chunks[nseg], total_elems, chunks[nchunks] as CHUNK_DTYPE records)."""
     numel = np.ascontiguousarray(numels, dtype=np.int64)
     n = int(numel.size)
     off = np.zeros(n, np.int64)
@@ -168,10 +173,10 @@ def plan_layout(numels):
     l = lib()
     check(l.bnnp_plan_layout(numel.ctypes.data, n, off.ctypes.data, first.ctypes.data, nch.ctypes.data,
                              C.byref(total), C.byref(chunks), None), "bnnp_plan_layout")
-    chunk_seg = np.zeros(max(chunks.value, 1), np.int32)
+    table = np.zeros(max(chunks.value, 1), CHUNK_DTYPE)
     check(l.bnnp_plan_layout(numel.ctypes.data, n, off.ctypes.data, first.ctypes.data, nch.ctypes.data,
-                             C.byref(total), C.byref(chunks), chunk_seg.ctypes.data), "bnnp_plan_layout")
-    return off, first, nch, int(total.value), chunk_seg[:chunks.value]
+                             C.byref(total), C.byref(chunks), table.ctypes.data), "bnnp_plan_layout")
+    return off, first, nch, int(total.value), table[:chunks.value]
 
 
 # ---- Philox key schedule (specified in oracle/sgmcmc_oracle.py:philox_key) -------------

@@ -564,6 +564,21 @@ __device__ void apply_pending(const BnnpLaunch& L, const BnnpSegment& sd, int se
     __syncthreads();   // s_sum is reused by the caller
 }
 
+// one 128-bit load of a BnnpChunk
+struct ChunkDesc {
+    int64_t fbase;
+    int rem, seg;
+};
+static_assert(sizeof(BnnpChunk) == 16, "BnnpChunk is read with one 128-bit access");
+__device__ __forceinline__ ChunkDesc load_chunk(const BnnpChunk* chunks, int chunk) {
+    const int4 raw = *reinterpret_cast<const int4*>(chunks + chunk);
+    ChunkDesc d;
+    d.fbase = (int64_t)(((uint64_t)(uint32_t)raw.y << 32) | (uint64_t)(uint32_t)raw.x);
+    d.rem = raw.z;
+    d.seg = raw.w;
+    return d;
+}
+
 struct ChunkCtx {
     int64_t fbase;   // flat index of the chunk's first float
     int rem;         // valid floats in this chunk
@@ -625,16 +640,15 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     const int tid = threadIdx.x;
     const int slot = (L.flags & BNNP_F_REVERSE) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
     const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[slot] : slot;
-    const int seg = L.chunk_seg[chunk];
+    const ChunkDesc cd = load_chunk(L.chunks, chunk);
+    const int seg = cd.seg;
     const BnnpSegment sd = L.segs[seg];
     // the previous launch's bookkeeping: segment j is handled by CTA j, i.e. by the CTAs that
     // start first, so the few microseconds it takes are absorbed at the front of the launch
     if (L.pending.valid && (int)blockIdx.x < L.nseg) apply_pending(L, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
-    const int64_t cbase = (int64_t)(chunk - sd.first_chunk) * CHUNK;
-    const int64_t left = sd.numel - cbase;
     ChunkCtx cx;
-    cx.rem = left < (int64_t)CHUNK ? (int)left : CHUNK;
-    cx.fbase = sd.off + cbase;
+    cx.rem = cd.rem;
+    cx.fbase = cd.fbase;
     cx.tid = tid;
     const uint32_t flags = L.flags;
 
@@ -750,14 +764,13 @@ __global__ void __launch_bounds__(THREADS, BNNP_PREPASS_CTAS) bnnp_prepass_kerne
     const BnnpLaunch& L = S.L;
     const int tid = threadIdx.x;
     const int chunk = (L.flags & BNNP_F_REVERSE) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-    const int seg = L.chunk_seg[chunk];
+    const ChunkDesc cd = load_chunk(L.chunks, chunk);
+    const int seg = cd.seg;
     BnnpSegment sd = L.segs[seg];
     if (L.pending.valid && (int)blockIdx.x < L.nseg) apply_pending(L, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
-    const int64_t cbase = (int64_t)(chunk - sd.first_chunk) * CHUNK;
-    const int64_t left = sd.numel - cbase;
     ChunkCtx cx;
-    cx.rem = left < (int64_t)CHUNK ? (int)left : CHUNK;
-    cx.fbase = sd.off + cbase;
+    cx.rem = cd.rem;
+    cx.fbase = cd.fbase;
     cx.tid = tid;
 
     F4 p[UNROLL];
@@ -917,7 +930,7 @@ int bnnp_max_ctas_per_sm(int noise, int has_prior, int noise_first, int sums, in
 }
 
 int bnnp_plan_layout(const int64_t* numel, int nseg, int64_t* off, int32_t* first_chunk, int32_t* num_chunks,
-                     int64_t* total_elems, int32_t* total_chunks, int32_t* chunk_seg) {
+                     int64_t* total_elems, int32_t* total_chunks, BnnpChunk* chunks) {
     if (numel == nullptr || nseg < 0 || off == nullptr || first_chunk == nullptr || num_chunks == nullptr)
         return fail(BNNP_E_ARG, "bnnp_plan_layout: null argument");
     int64_t o = 0, ch = 0;
@@ -928,8 +941,13 @@ int bnnp_plan_layout(const int64_t* numel, int nseg, int64_t* off, int32_t* firs
         off[i] = o;
         first_chunk[i] = (int32_t)ch;
         num_chunks[i] = (int32_t)nch;
-        if (chunk_seg != nullptr)
-            for (int64_t k = 0; k < nch; ++k) chunk_seg[ch + k] = i;
+        if (chunks != nullptr)
+            for (int64_t k = 0; k < nch; ++k) {
+                const int64_t left = numel[i] - k * BNNP_CHUNK;
+                chunks[ch + k].fbase = o + k * BNNP_CHUNK;
+                chunks[ch + k].rem = left < (int64_t)BNNP_CHUNK ? (int32_t)left : BNNP_CHUNK;
+                chunks[ch + k].seg = i;
+            }
         ch += nch;
         o += (numel[i] + BNNP_SEG_ALIGN - 1) / BNNP_SEG_ALIGN * BNNP_SEG_ALIGN;
     }
@@ -941,7 +959,7 @@ int bnnp_plan_layout(const int64_t* numel, int nseg, int64_t* off, int32_t* firs
 int bnnp_launch(const BnnpLaunch* a, void* stream) {
     if (a == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: null args");
     if (a->nseg <= 0 || a->nchunks <= 0) return fail(BNNP_E_ARG, "bnnp_launch: empty chain");
-    if (a->segs == nullptr || a->chunk_seg == nullptr || a->seg_state == nullptr || a->partials == nullptr ||
+    if (a->segs == nullptr || a->chunks == nullptr || a->seg_state == nullptr || a->partials == nullptr ||
         a->stamps == nullptr)
         return fail(BNNP_E_ARG, "bnnp_launch: null table pointer");
     if (a->nchunks > a->nchunks_total || (a->chunk_ids == nullptr && a->nchunks != a->nchunks_total))
@@ -964,8 +982,8 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
     if (a->noise == BNNP_NOISE_REPLAY && a->replay_noise == nullptr)
         return fail(BNNP_E_ARG, "bnnp_launch: replay noise is null");
     if (misaligned(a->P) || misaligned(a->G) || misaligned(a->M) || misaligned(a->prev_p) || misaligned(a->prev_g) ||
-        misaligned(a->prev_m) || misaligned(a->replay_noise))
-        return fail(BNNP_E_ALIGN, "bnnp_launch: flat arrays must be 16-byte aligned");
+        misaligned(a->prev_m) || misaligned(a->replay_noise) || misaligned(a->chunks))
+        return fail(BNNP_E_ALIGN, "bnnp_launch: flat arrays and the chunk table must be 16-byte aligned");
     if (a->pending.valid && (a->pending.flags & BNNP_F_HYPER))
         return fail(BNNP_E_ARG, "bnnp_launch: the epilogue of a BNNP_F_HYPER launch rewrites the segment table; "
                                 "bnnp_finalize first");

@@ -141,10 +141,10 @@ class FlatGroup:
         self.lib = N.lib()
         self.numel = [int(p.numel()) for p in self.params]
         self.nseg = len(self.params)
-        off, first, nch, total, chunk_seg = N.plan_layout(self.numel)
+        off, first, nch, total, chunks = N.plan_layout(self.numel)
         self.off = [int(o) for o in off]
         self.total = total
-        self.nchunks = int(chunk_seg.size)
+        self.nchunks = int(chunks.size)
         self.n_params = int(sum(self.numel))
 
         # segment table (host copy + device copy)
@@ -156,8 +156,8 @@ class FlatGroup:
         self.table["link"] = -1
         self.table_dev = torch.empty(self.table.nbytes, dtype=torch.uint8, device=dev)
         self._table_dirty = True
-        self.chunk_seg_host = np.ascontiguousarray(chunk_seg)
-        self.chunk_seg_dev = torch.from_numpy(self.chunk_seg_host).to(dev)
+        self.chunk_seg_host = np.ascontiguousarray(chunks["seg"])
+        self.chunks_dev = torch.from_numpy(np.ascontiguousarray(chunks).view(np.uint8).copy()).to(dev)   # BnnpChunk[nchunks]
 
         # flat arrays
         self.P = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -417,7 +417,7 @@ class FlatGroup:
     def _table_pointers(self, a) -> None:
         if self._tables_set:
             return
-        a.segs, a.chunk_seg = self.table_dev.data_ptr(), self.chunk_seg_dev.data_ptr()
+        a.segs, a.chunks = self.table_dev.data_ptr(), self.chunks_dev.data_ptr()
         a.seg_state, a.partials, a.stamps = self.state_dev.data_ptr(), self.partials.data_ptr(), self.stamps.data_ptr()
         a.nseg, a.nchunks_total = self.nseg, self.nchunks
         self._tables_set = True

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BNNP_ABI_VERSION 6
+#define BNNP_ABI_VERSION 7
 
 #define BNNP_SEG_ALIGN 32      /* floats: every segment starts on a 128-byte line */
 #ifndef BNNP_THREADS
@@ -174,6 +174,16 @@ typedef struct BnnpSegment {
     int32_t reserved;
 } BnnpSegment;
 
+/* One chunk of BNNP_CHUNK floats (the work of one CTA), 16 bytes: what a CTA needs before it
+ * can issue its loads, in one 128-bit access (the segment descriptor is fetched in parallel
+ * with the data instead of in front of it). */
+typedef struct BnnpChunk {
+    int64_t fbase;       /* flat index of the chunk's first float                */
+    int32_t rem;         /* valid floats in this chunk (BNNP_CHUNK except at the
+                            end of a segment)                                   */
+    int32_t seg;         /* segment the chunk belongs to                        */
+} BnnpChunk;
+
 /* What the per-segment scalar bookkeeping (the "epilogue") of a launch needs.  It is
  * not applied by the launch itself but by the NEXT bnnp_launch on the same chain
  * (which receives it as BnnpLaunch.pending; its first nseg CTAs do the work) or by
@@ -199,7 +209,7 @@ typedef struct BnnpLaunch {
     const float* replay_noise; /* flat [total], BNNP_NOISE_REPLAY                   */
     BnnpSegment* segs;         /* [nseg]; only the epilogue of a BNNP_F_HYPER launch
                                   writes it (prior_scale of linked segments)        */
-    const int32_t* chunk_seg;  /* [all chunks]: segment of every chunk              */
+    const BnnpChunk* chunks;   /* [all chunks], 16-byte aligned (bnnp_plan_layout)  */
     const int32_t* chunk_ids;  /* null: process chunks 0..nchunks-1; else [nchunks]
                                   chunk indices, whole segments only (used to skip
                                   tensors without a gradient, sgld.py:96-101)       */
@@ -237,11 +247,11 @@ int bnnp_max_ctas_per_sm(int noise, int has_prior, int noise_first, int sums, in
 
 /* Host helper (no GPU needed): flat-layout offsets and chunk table for `nseg`
  * tensors.  Fills off[nseg], first_chunk[nseg], num_chunks[nseg]; returns the
- * totals.  chunk_seg may be null; otherwise it must hold *total_chunks ints
+ * totals.  chunks may be null; otherwise it must hold *total_chunks records
  * (call once with null to size it). */
 int bnnp_plan_layout(const int64_t* numel, int nseg,
                      int64_t* off, int32_t* first_chunk, int32_t* num_chunks,
-                     int64_t* total_elems, int32_t* total_chunks, int32_t* chunk_seg);
+                     int64_t* total_elems, int32_t* total_chunks, BnnpChunk* chunks);
 
 /* The one hot kernel.  Replaces, depending on op/phase/flags:
  *   SGLD._step_fn            mcmc/sgld.py:119-154

@@ -131,7 +131,8 @@ def test_struct_layouts_match_header():
 
 def test_plan_layout(lib):
     numel = [10, 4096, 4097, 1, 39200, 31]
-    off, first, nch, total, chunk_seg = N.plan_layout(numel)
+    off, first, nch, total, chunks = N.plan_layout(numel)
+    chunk_seg = chunks["seg"]
     assert list(nch) == [1, 1, 2, 1, 10, 1]
     assert list(first) == [0, 1, 2, 4, 5, 15]
     assert all(o % N.SEG_ALIGN == 0 for o in off)
@@ -139,6 +140,10 @@ def test_plan_layout(lib):
         assert off[i + 1] - off[i] >= numel[i] and off[i + 1] - off[i] < numel[i] + N.SEG_ALIGN
     assert total % N.SEG_ALIGN == 0 and total >= off[-1] + numel[-1]
     assert list(chunk_seg) == [0, 1, 2, 2, 3] + [4] * 10 + [5]
+    # BnnpChunk: first float and valid floats of every chunk
+    assert list(chunks["rem"][:5]) == [10, 4096, 4096, 1, 1] and chunks["rem"][14] == 39200 - 9 * 4096 and chunks["rem"][15] == 31
+    assert list(chunks["fbase"][:5]) == [off[0], off[1], off[2], off[2] + 4096, off[3]]
+    assert N.CHUNK_DTYPE.itemsize == 16 and "typedef struct BnnpChunk" in HEADER
     # empty segments are rejected with a message, not a crash
     bad = np.array([4, 0], dtype=np.int64)
     o, f, n = np.zeros(2, np.int64), np.zeros(2, np.int32), np.zeros(2, np.int32)
@@ -152,7 +157,7 @@ def test_launch_validates_arguments_without_a_gpu(lib):
     assert lib.bnnp_launch(C.byref(a), None) == -1 and b"empty chain" in lib.bnnp_last_error()
     a.nseg, a.nchunks, a.nchunks_total = 1, 1, 1
     assert lib.bnnp_launch(C.byref(a), None) == -1 and b"null table" in lib.bnnp_last_error()
-    for f in ("segs", "chunk_seg", "seg_state", "partials", "stamps"):   # chunk_ids may stay null
+    for f in ("segs", "chunks", "seg_state", "partials", "stamps"):   # chunk_ids may stay null
         setattr(a, f, 4096)
     a.nchunks = 2
     assert lib.bnnp_launch(C.byref(a), None) == -1 and b"does not match the plan" in lib.bnnp_last_error()
