@@ -178,6 +178,28 @@ def time_cpu(steps: int, warmup: int, threads: int):
     return dt / steps, n_params, len(chains)
 
 
+def time_cpu_torch(steps: int, warmup: int, threads: int):
+    """Seconds per step of the reference's own op sequence (oracle/sgmcmc_torch.py: one tensor at
+    a time, in-place ATen CPU kernels with intra-op threading, torch.randn_like for the noise)."""
+    import torch
+    from oracle import sgmcmc_torch as OT
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    tensors = load_tensors()
+    params = [torch.randn(tuple(t["shape"]), generator=g) * (t["scale"] if t["kind"] else 1.0) for t in tensors]
+    ch = OT.TorchSGLDChain(params, **HP)
+    for t in ch.g:
+        t.normal_(0.0, 1e-3, generator=g)
+    ch.sample_momentum()
+    for _ in range(warmup):
+        ch.step(calc_metrics=False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ch.step(calc_metrics=False)
+    dt = time.perf_counter() - t0
+    return dt / steps, sum(int(p.numel()) for p in params)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -185,16 +207,27 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     steps = max(1, min(args.steps, 40))
     warmup = max(1, min(args.warmup, 3))
-    sec, n_params, used = time_cpu(steps, warmup, threads)
+    # (a) the numpy port, the 25M chain cut into one sub-chain per host thread (parallel noise)
+    sec_np, n_params, used = time_cpu(steps, warmup, threads)
+    # (b) the reference's own torch op sequence, all host threads for ATen's intra-op parallelism;
+    #     bounded: its serial randn_like makes a step take ~0.3 s
+    t_steps = max(2, min(steps, 12))
+    sec_t, _ = time_cpu_torch(t_steps, 1, threads)
+    arms = {"numpy_port_one_subchain_per_thread": {"ms_per_step": sec_np * 1e3, "value": n_params / sec_np, "steps": steps},
+            "torch_ops_like_the_reference": {"ms_per_step": sec_t * 1e3, "value": n_params / sec_t, "steps": t_steps}}
+    # headline of this arm: the FASTER of the two (the stronger CPU baseline)
+    best = min(arms, key=lambda k: arms[k]["ms_per_step"])
+    sec = arms[best]["ms_per_step"] * 1e-3
     value = n_params / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": arms[best]["steps"], "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_params": n_params, "sampler": "SGLD", **HP,
-                   "note": "reference algorithm's CPU port (oracle/sgmcmc_oracle.py, numpy), one sub-chain per host thread"},
+                   "note": "CPU arms of the reference algorithm on the host cores; value = the faster one (" + best + ")"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
-                         "sample": f"{steps} full SGLD steps over all {n_params} parameters"},
+                         "sample": f"{arms[best]['steps']} full SGLD steps over all {n_params} parameters ({best})"},
+        "cpu_arms": arms,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

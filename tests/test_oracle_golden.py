@@ -146,3 +146,32 @@ def test_oracle_hierarchical_prior_matches_reference_autograd(case):
     got_p, got_u = -ch.segs[0].g, -float(ch.segs[1].g[0])
     assert np.allclose(got_p, g_ref, rtol=2e-5, atol=1e-6 * np.abs(g_ref).max())
     assert math.isclose(got_u, case["grad_u"], rel_tol=2e-5, abs_tol=1e-4), (got_u, case["grad_u"])
+
+
+def test_torch_op_restatement_agrees_with_the_numpy_oracle():
+    """oracle/sgmcmc_torch.py (the CPU arm of bench.py) against oracle/sgmcmc_oracle.py on
+    seeded inputs: same noise, same gradients, a few steps."""
+    import torch
+    from oracle import sgmcmc_torch as OT
+    rng = np.random.default_rng(5)
+    shapes = [(257,), (8, 5), (5,), (33, 3)]
+    p0 = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    hp = dict(lr=1e-2, num_data=50.0, momentum=0.9, temperature=0.7)
+    ch = O.Chain(p0, O.Group(**hp))
+    tc = OT.TorchSGLDChain([torch.tensor(a) for a in p0], **hp)
+    z = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    O.sample_momentum(ch, lambda i, n: z[i].reshape(-1))
+    tc.sample_momentum(noise=[torch.tensor(a) for a in z])
+    for it in range(6):
+        gs = [rng.standard_normal(s).astype(np.float32) * 0.1 for s in shapes]
+        z = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+        for seg, g, tg in zip(ch.segs, gs, tc.g):
+            seg.g = g.reshape(-1).copy()
+            tg.copy_(torch.tensor(g))
+        O.sgld_step(ch, lambda i, n: z[i].reshape(-1), calc_metrics=True)
+        tc.step(calc_metrics=True, noise=[torch.tensor(a) for a in z])
+        for i, seg in enumerate(ch.segs):
+            assert np.allclose(tc.p[i].numpy().reshape(-1), seg.p, rtol=1e-5, atol=1e-6)   # fp32, fused vs separate roundings
+            assert np.allclose(tc.m[i].numpy().reshape(-1), seg.m, rtol=1e-5, atol=1e-6)
+            assert math.isclose(tc.est_temperature[i], seg.est_temperature, rel_tol=1e-5)
+            assert math.isclose(tc.est_config_temp[i], seg.est_config_temp, rel_tol=1e-4, abs_tol=1e-6)
