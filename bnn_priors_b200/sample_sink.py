@@ -10,10 +10,13 @@ copy per tensor, 175 of them for `googleresnet` -- and then appending to an HDF5
 parameter array: a sample is ONE device-to-device snapshot of P (plus one packed copy
 of the few non-parameter buffers) on the compute stream and ONE asynchronous
 device-to-host copy into pinned memory on a side stream, so the chain never waits for
-the host.  The result is written with `torch.save` as `{name: [n_samples, *shape],
-"steps": int64[n], "timestamps": float64[n]}` -- the layout the reference's
-`load_samples` reads through its `torch.load` fallback (exp_utils.py:539-551; h5py is
-not available here, and the HDF5 writer itself stays out of scope).
+the host.  The result is `{name: [n_samples, *shape], "steps": int64[n], "timestamps":
+float64[n]}`.  Where h5py is installed it is written as the reference's HDF5 file --
+one dataset per key, shape [n, *shape], chunks (1, *shape), maxshape (None, *shape),
+fletcher32, NaN fill value, `libver="latest"` (exp_utils.py:418-421,467-477) -- so
+`load_samples` and `experiments/eval_bnn.py` read it unchanged; otherwise (this image
+has no h5py) with `torch.save`, which `load_samples` reads through its `torch.load`
+fallback (exp_utils.py:539-551).  The HDF5 library itself is not re-implemented.
 """
 from __future__ import annotations
 
@@ -21,6 +24,30 @@ import time
 from typing import Dict, List, Optional
 
 import torch
+
+
+def write_samples_hdf5(path: str, samples: Dict[str, torch.Tensor], h5py_module) -> None:
+    """The file HDF5ModelSaver leaves behind (exp_utils.py:409-477), written in one go."""
+    import numpy as np
+    with h5py_module.File(path, "w", libver="latest") as f:
+        for k, v in samples.items():
+            a = v.detach().cpu().numpy()
+            if a.dtype not in (np.float32, np.float64, np.int64):
+                raise TypeError(f"{k}: float32, float64 and int64 only (exp_utils.py:467-469), got {a.dtype}")
+            shape = tuple(a.shape[1:])
+            d = f.create_dataset(k, dtype=a.dtype, shape=(0,) + shape, chunks=(1,) + shape,
+                                 maxshape=(None,) + shape, fletcher32=True, fillvalue=np.nan)
+            d.resize(a.shape[0], axis=0)
+            d[0:a.shape[0]] = a
+        f.flush()
+
+
+def _h5py_or_none():
+    try:
+        import h5py
+        return h5py if hasattr(h5py, "File") else None
+    except ImportError:
+        return None
 
 
 class FlatSampleSaver:
@@ -122,7 +149,11 @@ class FlatSampleSaver:
                 e.synchronize()
             self._events.clear()
             if self.path is not None and self.count:
-                torch.save(self.load_samples(keep_steps=True), self.path)
+                h5 = _h5py_or_none()
+                if h5 is not None and not str(self.path).endswith((".pt", ".pth")):
+                    write_samples_hdf5(self.path, self.load_samples(keep_steps=True), h5)
+                else:
+                    torch.save(self.load_samples(keep_steps=True), self.path)
 
     def load_samples(self, idx=slice(None), keep_steps: bool = True) -> Dict[str, torch.Tensor]:
         """Same result layout as exp_utils.load_samples (exp_utils.py:539-551)."""
