@@ -293,97 +293,121 @@ def golden_hmc():
     rec.save("hmc_trace")
 
 
-def golden_runner():
-    """The reference's own VerletSGLDRunnerReject (inference_reject.py:11-176)
-    driving a recording VerletSGLD on a reference ClassificationDenseNet with
-    Normal / Laplace / StudentT priors, synthetic data.  This pins the call
-    ORDER the runner produces and the prior's contribution to p.grad."""
+def _golden_runner_case(tag, runner_cls, sampler_name, prior_w, wparams, runner_kw, out_name):
+    """One reference runner driving a recording sampler on a reference ClassificationDenseNet,
+    synthetic data.  Pins the call ORDER the runner produces and the prior's contribution to
+    p.grad."""
     from bnn_priors import prior as ref_prior
     from bnn_priors.models import ClassificationDenseNet
-    from bnn_priors import inference_reject
 
+    torch.manual_seed(1005)
+    n, din, width, dout = 96, 20, 16, 4
+    x = torch.rand(n, din)
+    y = torch.randint(0, dout, (n,))
+    model = ClassificationDenseNet(din, dout, width, depth=3, prior_w=prior_w,
+                                   weight_prior_params=wparams)
+    ds = torch.utils.data.TensorDataset(x, y)
+    dl = torch.utils.data.DataLoader(ds, batch_size=32, shuffle=True)
+    dl_test = torch.utils.data.DataLoader(ds, batch_size=96)
+
+    class NullMetrics:
+        def add_scalar(self, *a, **k): pass
+        def flush(self, *a, **k): pass
+
+    holder = {}
+    prior_of = {id(pm.p): pm for _, pm in ref_prior.named_priors(model)}
+    KIND = {"Normal": 1, "Laplace": 2, "StudentT": 3}
+
+    Base = getattr(ref_mcmc, sampler_name)
+
+    class Recording(Base):
+        """Routes the runner's calls through the Recorder."""
+        def __init__(self, params, **kw):
+            super().__init__(params, **kw)
+            ps = [p for g in self.param_groups for p in g["params"]]
+            specs = []
+            for p in ps:
+                pm = prior_of[id(p)]
+                specs.append(dict(kind=KIND[type(pm).__name__], loc=float(pm.loc),
+                                  scale=float(pm.scale),
+                                  df=float(getattr(pm, "df", torch.tensor(3.0)))))
+            rec = Recorder(self, sampler_name, {k: float(v) for k, v in kw.items()},
+                           extra_meta=dict(priors=specs, runner=runner_cls.__name__))
+
+            def grad_prior():
+                with torch.enable_grad():
+                    gs = torch.autograd.grad(-model.log_prior() / kw["num_data"], ps)
+                return np.concatenate([g.reshape(-1).numpy() for g in gs]).astype(np.float32)
+            rec.grad_prior_fn = grad_prior
+            holder["rec"] = rec
+            self._in_call = False
+
+        def _wrap(name):
+            def f(self, *a, **k):
+                if getattr(self, "_in_call", True):
+                    return getattr(Base, name)(self, *a, **k)
+                self._in_call = True
+                try:
+                    return holder["rec"].call(name, *a, **k)
+                finally:
+                    self._in_call = False
+            return f
+        for _n in ("sample_momentum", "initial_step", "step", "final_step",
+                   "delta_energy", "maybe_reject", "update_preconditioner"):
+            if hasattr(Base, _n):
+                locals()[_n] = _wrap(_n)
+
+    class DetGenerator(torch.Generator):
+        def seed(self):          # inference_reject.py:72 would use OS entropy
+            self.manual_seed(4242)
+            return 4242
+
+    saved_cls, saved_gen = getattr(ref_mcmc, sampler_name), torch.Generator
+    setattr(ref_mcmc, sampler_name, Recording)
+    torch.Generator = DetGenerator
+    try:
+        runner = runner_cls(model=model, dataloader=dl, dataloader_test=dl_test,
+                            metrics_saver=NullMetrics(), model_saver=None, **runner_kw)
+        # the constructor's update_preconditioner happened before recording
+        runner.run(progressbar=False)
+    finally:
+        setattr(ref_mcmc, sampler_name, saved_cls)
+        torch.Generator = saved_gen
+    rec = holder["rec"]
+    ops = [e["op"] for e in rec.events]
+    print("  runner", tag, "ops:", {o: ops.count(o) for o in sorted(set(ops))},
+          "rejects:", sum(1 for e in rec.events if e["op"] == "maybe_reject" and e["out"][0]))
+    rec.save(out_name)
+
+
+def golden_runner():
+    """The reference's own VerletSGLDRunnerReject (inference_reject.py:11-176) with Normal /
+    Laplace / StudentT priors (the analogs of BASELINE configs 2-4)."""
+    from bnn_priors import prior as ref_prior
+    from bnn_priors import inference_reject
+    kw = dict(epochs_per_cycle=4, warmup_epochs=1, sample_epochs=2, learning_rate=0.02, skip=1, metrics_skip=2,
+              temperature=1.0, momentum=0.9, cycles=2, precond_update=2, reject_samples=True)
     for tag, prior_w, wparams in (("normal", ref_prior.Normal, {}),
                                   ("laplace", ref_prior.Laplace, {}),
                                   ("studentt", ref_prior.StudentT, {"df": 3.0})):
-        torch.manual_seed(1005)
-        n, din, width, dout = 96, 20, 16, 4
-        x = torch.rand(n, din)
-        y = torch.randint(0, dout, (n,))
-        model = ClassificationDenseNet(din, dout, width, depth=3, prior_w=prior_w,
-                                       weight_prior_params=wparams)
-        ds = torch.utils.data.TensorDataset(x, y)
-        dl = torch.utils.data.DataLoader(ds, batch_size=32, shuffle=True)
-        dl_test = torch.utils.data.DataLoader(ds, batch_size=96)
+        _golden_runner_case(tag, inference_reject.VerletSGLDRunnerReject, "VerletSGLD", prior_w, wparams, kw,
+                            f"runner_verlet_{tag}_trace")
 
-        class NullMetrics:
-            def add_scalar(self, *a, **k): pass
-            def flush(self, *a, **k): pass
 
-        holder = {}
-        prior_of = {id(pm.p): pm for _, pm in ref_prior.named_priors(model)}
-        KIND = {"Normal": 1, "Laplace": 2, "StudentT": 3}
-
-        BaseVerlet = ref_mcmc.VerletSGLD
-
-        class RecordingVerlet(BaseVerlet):
-            """Routes the runner's calls through the Recorder."""
-            def __init__(self, params, **kw):
-                super().__init__(params, **kw)
-                ps = [p for g in self.param_groups for p in g["params"]]
-                specs = []
-                for p in ps:
-                    pm = prior_of[id(p)]
-                    specs.append(dict(kind=KIND[type(pm).__name__], loc=float(pm.loc),
-                                      scale=float(pm.scale),
-                                      df=float(getattr(pm, "df", torch.tensor(3.0)))))
-                rec = Recorder(self, "VerletSGLD", {k: float(v) for k, v in kw.items()},
-                               extra_meta=dict(priors=specs, runner="VerletSGLDRunnerReject"))
-
-                def grad_prior():
-                    with torch.enable_grad():
-                        gs = torch.autograd.grad(-model.log_prior() / kw["num_data"], ps)
-                    return np.concatenate([g.reshape(-1).numpy() for g in gs]).astype(np.float32)
-                rec.grad_prior_fn = grad_prior
-                holder["rec"] = rec
-                self._in_call = False
-
-            def _wrap(name):
-                def f(self, *a, **k):
-                    if getattr(self, "_in_call", True):
-                        return getattr(BaseVerlet, name)(self, *a, **k)
-                    self._in_call = True
-                    try:
-                        return holder["rec"].call(name, *a, **k)
-                    finally:
-                        self._in_call = False
-                return f
-            for _n in ("sample_momentum", "initial_step", "step", "final_step",
-                       "delta_energy", "maybe_reject", "update_preconditioner"):
-                locals()[_n] = _wrap(_n)
-
-        class DetGenerator(torch.Generator):
-            def seed(self):          # inference_reject.py:72 would use OS entropy
-                self.manual_seed(4242)
-                return 4242
-
-        saved_cls, saved_gen = ref_mcmc.VerletSGLD, torch.Generator
-        ref_mcmc.VerletSGLD = RecordingVerlet
-        torch.Generator = DetGenerator
-        try:
-            runner = inference_reject.VerletSGLDRunnerReject(
-                model=model, dataloader=dl, dataloader_test=dl_test, epochs_per_cycle=4,
-                warmup_epochs=1, sample_epochs=2, learning_rate=0.02, skip=1, metrics_skip=2,
-                temperature=1.0, momentum=0.9, cycles=2, precond_update=2,
-                metrics_saver=NullMetrics(), model_saver=None, reject_samples=True)
-            # the constructor's update_preconditioner happened before recording
-            runner.run(progressbar=False)
-        finally:
-            ref_mcmc.VerletSGLD, torch.Generator = saved_cls, saved_gen
-        rec = holder["rec"]
-        ops = [e["op"] for e in rec.events]
-        print("  runner", tag, "ops:", {o: ops.count(o) for o in sorted(set(ops))},
-              "rejects:", sum(1 for e in rec.events if e["op"] == "maybe_reject" and e["out"][0]))
-        rec.save(f"runner_verlet_{tag}_trace")
+def golden_runner_more():
+    """HMCRunnerReject (inference_reject.py:182-189; BASELINE config 5: leapfrog trajectories with
+    an M-H test per sampling epoch) and the plain SGLDRunner (inference.py:9-294; config 1)."""
+    from bnn_priors import prior as ref_prior
+    from bnn_priors import inference, inference_reject
+    _golden_runner_case("hmc_normal", inference_reject.HMCRunnerReject, "HMC", ref_prior.Normal, {},
+                        dict(epochs_per_cycle=3, warmup_epochs=1, sample_epochs=2, learning_rate=0.3, skip=1,
+                             metrics_skip=2, temperature=1.0, momentum=1.0, cycles=2, precond_update=2,
+                             reject_samples=True),
+                        "runner_hmc_normal_trace")
+    _golden_runner_case("sgld_normal", inference.SGLDRunner, "SGLD", ref_prior.Normal, {},
+                        dict(epochs_per_cycle=4, warmup_epochs=1, sample_epochs=2, learning_rate=0.02, skip=1,
+                             metrics_skip=2, temperature=1.0, momentum=0.9, cycles=2, precond_update=2),
+                        "runner_sgld_normal_trace")
 
 
 def golden_priors():
@@ -500,5 +524,6 @@ if __name__ == "__main__":
     golden_verlet()
     golden_hmc()
     golden_runner()
+    golden_runner_more()
     golden_priors()
     golden_hier_priors()

@@ -10,7 +10,9 @@ pytestmark = pytest.mark.gpu
 
 TRACES = ["sgld_trace", "sgld_nomomentum_trace", "verlet_trace", "hmc_trace",
           "runner_verlet_normal_trace", "runner_verlet_laplace_trace",
-          "runner_verlet_studentt_trace"]
+          "runner_verlet_studentt_trace",
+          # the reference's HMCRunnerReject and SGLDRunner (BASELINE configs 5 and 1)
+          "runner_hmc_normal_trace", "runner_sgld_normal_trace"]
 
 # north star: trajectories within 1e-5 relative fp32, accept decisions identical
 TRAJ_TOL = 1e-5

@@ -12,7 +12,9 @@ from replay import GOLDEN_DIR, OracleEngine, Trace, replay
 
 TRACES = ["sgld_trace", "sgld_nomomentum_trace", "verlet_trace", "hmc_trace",
           "runner_verlet_normal_trace", "runner_verlet_laplace_trace",
-          "runner_verlet_studentt_trace"]
+          "runner_verlet_studentt_trace",
+          # the reference's HMCRunnerReject and SGLDRunner (BASELINE configs 5 and 1)
+          "runner_hmc_normal_trace", "runner_sgld_normal_trace"]
 
 # fp32 elementwise work replayed op for op: a few ulp of drift over <=100 calls
 TRAJ_TOL = 1e-5
