@@ -7,6 +7,7 @@ import json
 import math
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -169,3 +170,54 @@ def test_sgd_known_answer_at_full_size():
     lo = min(means)
     for p, mval in zip(fg2.params, means):
         assert opt2.state[p]["preconditioner"] == pytest.approx((mval / lo) ** (-1 / 4), rel=1e-6)
+
+
+def test_flat_index_beyond_int32_known_answer():
+    """Maximum sizes: one tensor of 2^31 + 12,293 floats (8.6 GB; flat indices, Philox counters and
+    chunk bases beyond int32) between two small ones.  Known answers: SGD equivalence (the reference's
+    test_sgd_equivalence, testing/test_sgld.py:61-80: momentum 0, temperature 0 => p' = p - lr g) at
+    the far end of the big tensor and on the tensor after it; dot(g, g) against torch in float64;
+    the in-kernel noise at flat index > 2^31 against its specification."""
+    free, _ = torch.cuda.mem_get_info()
+    n_big = 2 ** 31 + 12293
+    if free < 5 * 4 * n_big:
+        pytest.skip("needs ~45 GB of free device memory")
+    from bnn_priors_b200 import _native as N
+    from bnn_priors_b200 import mcmc
+    from oracle import sgmcmc_oracle as O
+    g = torch.Generator(device=DEV).manual_seed(1)
+    params = [torch.nn.Parameter(torch.randn(100, device=DEV, generator=g)),
+              torch.nn.Parameter(torch.empty(n_big, device=DEV).normal_(0, 1, generator=g)),
+              torch.nn.Parameter(torch.randn(777, device=DEV, generator=g))]
+    lr, n_data = 0.25, 4.0
+    opt = mcmc.SGLD(params, lr=lr, num_data=n_data, momentum=0.0, temperature=0.0, seed=5)
+    (fg,) = opt.flat_groups
+    assert fg.off[2] > 2 ** 31 and fg.nchunks > 2 ** 19
+    for p, v in zip(params, fg.g_views):
+        p.grad = v
+    tail = slice(n_big - 5000, n_big)
+    fg.g_views[1][tail].normal_(0, 1, generator=g)
+    fg.g_views[1][:5000].normal_(0, 1, generator=g)
+    fg.g_views[2].normal_(0, 1, generator=g)
+    before_tail, before_last = params[1].detach()[tail].clone(), params[2].detach().clone()
+    g_tail, g_last = fg.g_views[1][tail].clone(), fg.g_views[2].clone()
+    gg = float((fg.g_views[1][tail].double() ** 2).sum() + (fg.g_views[1][:5000].double() ** 2).sum())
+    opt.step(calc_metrics=False)
+    # p' = p + h * (-hn * g) with h = sqrt(lr/N), hn = sqrt(lr N)  =>  p - lr g
+    assert torch.allclose(params[1].detach()[tail], before_tail - lr * g_tail, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(params[2].detach(), before_last - lr * g_last, rtol=1e-6, atol=1e-7)
+    assert math.isclose(float(fg.fetch()[1, N.S_SUM_GG]), gg, rel_tol=1e-6)
+    # noise beyond 2^31: sample_momentum writes eps * sqrt(T); compare the last quads with the specification
+    opt.param_groups[0]["temperature"] = 1.0
+    call = fg.call
+    opt.sample_momentum()
+    m = opt.state[params[1]]["momentum_buffer"].reshape(-1)
+    q0 = (fg.off[1] + n_big - 64) // 4 * 4
+    want = O.philox_normal_segment(fg.key, call, q0, 64)
+    got = fg.M[q0:q0 + 64].cpu().numpy()
+    valid = min(64, fg.off[1] + n_big - q0)
+    d = np.abs(got[:valid] - want[:valid])        # fast-math Box-Muller: same bounds as test_cuda_ops.py
+    assert d.max() < 2e-3 and d.mean() < 2e-5, (d.max(), d.mean())
+    assert m.shape[0] == n_big
+    del opt, params, fg
+    torch.cuda.empty_cache()
