@@ -231,7 +231,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------
@@ -430,10 +430,38 @@ def run_gpu(args):
     }
     if gather_ms is not None:
         line["cycle_gather_ms"] = gather_ms
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+class QuietStdout:
+    """Rank 0 must print exactly ONE line on stdout.  Libraries write there too (NCCL prints its
+    version banner to stdout when the first communicator comes up), so file descriptor 1 is pointed
+    at stderr for the whole run and the JSON line goes to the saved descriptor at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str) -> None:
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+OUT = None
+
+
+def emit(obj) -> None:
+    line = json.dumps(obj)
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
 
 
 def main():
+    global OUT
+    OUT = QuietStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
