@@ -21,6 +21,9 @@ import torch
 
 from .. import _native as N
 
+# BNNP_NVTX=1: an NVTX range around every launch (names the op / phase / flags in an nsys or ncu timeline)
+_NVTX = os.environ.get("BNNP_NVTX", "0") == "1"
+
 # keys of optimizer.state[p] whose values live on the device between launches
 LAZY_SCALARS = ("est_temperature", "est_config_temp", "delta_energy", "prev_new_momentum_delta")
 
@@ -440,11 +443,15 @@ class FlatGroup:
             # alternate the chunk order from launch to launch: each launch starts on the lines the
             # previous one left in L2 (include/bnnp.h: BNNP_F_REVERSE)
             a.flags = (a.flags | N.F_REVERSE) if self._parity else (a.flags & ~N.F_REVERSE)
+        if _NVTX:
+            torch.cuda.nvtx.range_push(f"bnnp_launch op={a.op} phase={a.phase} flags={a.flags:#x}")
         if torch.cuda.current_device() != self._dev_index:
             with torch.cuda.device(self.device):
                 rc = self.lib.bnnp_launch(C.byref(a), self._stream())
         else:
             rc = self.lib.bnnp_launch(C.byref(a), self._stream())
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
         N.check(rc, "bnnp_launch")
         self._pending = (a.op, a.phase, a.flags, self._parity, self.call, a.c_gm_base, a.curv_base, a.rms_alpha,
                          a.inv_num_data)
