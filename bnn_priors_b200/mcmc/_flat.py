@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -213,6 +214,7 @@ class FlatGroup:
         self.serpentine = os.environ.get("BNNP_SERPENTINE", "1") != "0"
         self.seg_states = [SegState(self, i) for i in range(self.nseg)]
         self._sync_rows = list(zip(self.params, self.g_views, self.p_views, self._p_ptrs))
+        self._g_seen: List[Optional[tuple]] = [None] * self.nseg     # (weakref to the foreign grad tensor, its version) last copied into G
         self.args = N.BnnpLaunch()
         self.launches = 0
 
@@ -232,11 +234,14 @@ class FlatGroup:
 
     @torch.no_grad()
     def sync_views(self, raise_on_no_grad: bool) -> List[int]:
-        """Make sure p, p.grad (and momentum_buffer) are still the flat views; copy
-        foreign tensors in if somebody re-bound them (closures that set
-        `p.grad = None`, `Prior.sample()`).  Returns the indices of parameters that
-        have no gradient (sgld.py:96-101)."""
+        """Bring the flat arrays up to date with what the model holds: a p.grad that is
+        not the flat view (after `zero_grad()` autograd stores every gradient in a tensor
+        of its own) is copied into G -- all of them with one multi-tensor copy --, a
+        parameter whose storage was swapped (`Prior.sample()`) is re-adopted.  Returns the
+        indices of parameters that have no gradient (sgld.py:96-101)."""
         missing: List[int] = []
+        dst: List[torch.Tensor] = []
+        src: List[torch.Tensor] = []
         i = 0
         for p, gv, pv, ptr in self._sync_rows:
             g = p.grad
@@ -251,14 +256,36 @@ class FlatGroup:
                         raise RuntimeError(f"No gradient for parameter with shape {p.shape}")
                     missing.append(i)
                 else:
-                    gv.copy_(g)
-                    p.grad = gv
+                    # a gradient autograd put into a tensor of its own (the usual case after
+                    # zero_grad(): p.grad was None and backward() stored its buffer there).  Copied
+                    # once: the same tensor at the same version is already in G, and G must not look
+                    # modified (with a fused prior the sums of the last step cannot be recomputed
+                    # once P has moved: the reference's p.grad holds the prior gradient at the OLD p)
+                    seen = self._g_seen[i]
+                    ver = g._version
+                    if seen is None or seen[0]() is not g or seen[1] != ver:
+                        dst.append(gv)
+                        src.append(g)
+                        self._g_seen[i] = (weakref.ref(g), ver)    # weak: the old gradient may be freed
             if p.data_ptr() != ptr:
                 pv.copy_(p.data)
                 p.data = pv
                 self._lp_valid = False
             i += 1
+        if dst:
+            try:
+                torch._foreach_copy_(dst, src)      # one multi-tensor launch instead of one copy per tensor
+            except (RuntimeError, TypeError):
+                for d, g in zip(dst, src):
+                    d.copy_(g)
         return missing
+
+    def bind_grad_views(self) -> None:
+        "p.grad <- its view of the flat G array, for every parameter"
+        for p, v in zip(self.params, self.g_views):
+            if p.grad is not v:
+                p.grad = v
+        self._g_seen = [None] * self.nseg
 
     def ensure_momentum_storage(self) -> None:
         if self.M is None:
@@ -600,3 +627,4 @@ class FlatGroup:
         N.check(rc, "bnnp_rollback")
         self.launches += 1
         self.invalidate_sums()
+        self.bind_grad_views()       # p.grad is the restored gradient again (verlet_sgld.py:66-67)

@@ -92,15 +92,19 @@ class SGLD(torch.optim.Optimizer):
             v = state['preconditioner'] = 1.
             return v
 
-    def zero_grad(self, set_to_none: bool = False):
-        """inference.py:216 calls this every minibatch.  The gradients are views of
-        the flat G array, so they are zeroed with one memset and never dropped
-        (torch's default set_to_none=True would detach the views)."""
+    def zero_grad(self, set_to_none: bool = True):
+        """inference.py:216 calls this every minibatch.  Like torch >= 2's default it drops the
+        gradients (`p.grad = None`): backward() then hands every gradient over in a fresh tensor
+        without an accumulation kernel, and the next sampler call copies all of them into the flat
+        G array with one multi-tensor copy (FlatGroup.sync_views).  `set_to_none=False` zeroes G
+        with one memset and binds p.grad to its views, so that autograd accumulates in place."""
         for fg in self._flat:
-            fg.G.zero_()
-            for p, v in zip(fg.params, fg.g_views):
-                if p.grad is not v:
-                    p.grad = v
+            if set_to_none:
+                for p in fg.params:
+                    p.grad = None
+            else:
+                fg.G.zero_()
+                fg.bind_grad_views()
 
     def delta_energy(self, a, b) -> float:
         return math.inf

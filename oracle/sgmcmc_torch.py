@@ -61,3 +61,36 @@ class TorchSGLDChain:
                 self.est_config_temp[i] = (p.view(-1) @ g.view(-1)).item() * (self.num_data / d)
             p.add_(m, alpha=h * M)
             sq.mul_(self.alpha).addcmul_(g, g, value=1 - self.alpha)
+
+
+class TorchVerletChain(TorchSGLDChain):
+    """The intermediate GGMC transition (bnn_priors/mcmc/verlet_sgld.py:138-197) with the
+    reference's ops: a fresh momentum tensor per step, two `.item()` dot products per tensor for the
+    delta-energy bookkeeping and two more for the diagnostics."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.delta_energy = [0.0] * len(self.p)
+        self.prev_new_momentum_delta = [0.0] * len(self.p)
+
+    @torch.no_grad()
+    def step(self, calc_metrics: bool = False, noise=None):
+        a = self.a
+        bh = math.sqrt(self.lr / self.num_data)
+        bhn = math.sqrt(self.lr * self.num_data)
+        mom_decay, grad_v, noise_std = a, 1 + a, math.sqrt((1 - a * a) * self.T)
+        for i, (p, g, m, sq) in enumerate(zip(self.p, self.g, self.m, self.sq)):
+            M = self.precond[i]
+            d = p.numel()
+            z = torch.randn_like(p) if noise is None else noise[i]
+            new_m = z.mul_(noise_std) if noise is None else z * noise_std
+            new_m.add_(g, alpha=-.5 * grad_v * bhn * M).add_(m, alpha=mom_decay)
+            c = -.5 * bhn * M
+            self.delta_energy[i] += self.prev_new_momentum_delta[i] + c * (g.view(-1) @ m.view(-1)).item()
+            self.prev_new_momentum_delta[i] = c * (g.view(-1) @ new_m.view(-1)).item()
+            if calc_metrics:
+                self.est_temperature[i] = (m.view(-1) @ m.view(-1)).item() / d
+                self.est_config_temp[i] = (p.view(-1) @ g.view(-1)).item() * (self.num_data / d)
+            self.m[i] = new_m
+            p.add_(new_m, alpha=bh * M)
+            sq.mul_(self.alpha).addcmul_(g, g, value=1 - self.alpha)

@@ -361,7 +361,7 @@ def test_views_survive_zero_grad_load_state_dict_and_schedulers():
     opt.sample_momentum()
     x = torch.randn(8, 64, device=DEV)
     for it in range(3):
-        opt.zero_grad()
+        opt.zero_grad(set_to_none=False)
         assert all(p.grad is v for p, v in zip(ps, fg.g_views)) and float(fg.G.abs().sum()) == 0.0
         lin(x).pow(2).sum().backward()                        # autograd accumulates into the flat views
         assert all(p.grad is v for p, v in zip(ps, fg.g_views)) and float(fg.G.abs().sum()) > 0.0
@@ -378,6 +378,57 @@ def test_views_survive_zero_grad_load_state_dict_and_schedulers():
     opt.step(calc_metrics=False)
     assert ps[0].data_ptr() == fg.p_views[0].data_ptr()
     assert abs(float(ps[0].detach().mean()) - 3.0) < 0.1
+
+
+def test_default_zero_grad_drops_gradients_and_step_copies_them_in():
+    """torch >= 2 semantics (what the reference's runner gets from `optimizer.zero_grad()`):
+    p.grad = None, backward() stores fresh tensors, the step copies them into G in one go;
+    same trajectory as accumulating into the views."""
+    mcmc = _mcmc()
+    torch.manual_seed(1)
+    nets = [torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Tanh(), torch.nn.Linear(17, 3)).to(DEV) for _ in range(2)]
+    nets[1].load_state_dict(nets[0].state_dict())
+    opts = [mcmc.VerletSGLD(list(n.parameters()), lr=1e-2, num_data=10, momentum=0.9, temperature=1.0, seed=4) for n in nets]
+    x = torch.randn(8, 33, device=DEV)
+    for o in opts:
+        o.sample_momentum()
+    for it in range(4):
+        for k, (n, o) in enumerate(zip(nets, opts)):
+            o.zero_grad(set_to_none=(k == 0))
+            if k == 0:
+                assert all(p.grad is None for p in n.parameters())
+            n(x).pow(2).sum().backward()
+            if k == 0:
+                (fg,) = o.flat_groups
+                assert all(p.grad is not v for p, v in zip(fg.params, fg.g_views))
+            o.step(calc_metrics=(it == 2))
+        for p0, p1 in zip(nets[0].parameters(), nets[1].parameters()):
+            assert torch.equal(p0, p1)
+        assert torch.equal(opts[0].flat_groups[0].G, opts[1].flat_groups[0].G)
+    # gradient accumulation over several backward calls without zero_grad (inference_reject.py:18-33)
+    opts[0].zero_grad()
+    for _ in range(3):
+        nets[0](x).pow(2).sum().backward()
+    opts[1].zero_grad(set_to_none=False)
+    for _ in range(3):
+        nets[1](x).pow(2).sum().backward()
+    for o in opts:
+        o.step(calc_metrics=False)
+    for p0, p1 in zip(nets[0].parameters(), nets[1].parameters()):
+        assert torch.allclose(p0, p1, rtol=1e-6, atol=1e-7)
+    # after a rejection p.grad is the restored gradient (the flat view)
+    o = opts[0]
+    o.zero_grad()
+    nets[0](x).pow(2).sum().backward()
+    o.initial_step(save_state=True)
+    o.zero_grad()
+    nets[0](x).pow(2).sum().backward()
+    o.final_step()
+    torch.manual_seed(0)
+    rejected, _ = o.maybe_reject(1e9)
+    (fg,) = o.flat_groups
+    assert rejected and all(p.grad is v for p, v in zip(fg.params, fg.g_views))
+    assert torch.equal(fg.G, fg.prev_g)
 
 
 def test_two_param_groups():

@@ -177,3 +177,30 @@ def test_torch_op_restatement_agrees_with_the_numpy_oracle():
             assert np.allclose(tc.m[i].numpy().reshape(-1), seg.m, rtol=1e-5, atol=1e-6)
             assert math.isclose(tc.est_temperature[i], seg.est_temperature, rel_tol=1e-5)
             assert math.isclose(tc.est_config_temp[i], seg.est_config_temp, rel_tol=1e-4, abs_tol=1e-6)
+
+
+def test_torch_op_verlet_restatement_agrees_with_the_numpy_oracle():
+    import torch
+    from oracle import sgmcmc_torch as OT
+    rng = np.random.default_rng(6)
+    shapes = [(130,), (7, 6), (3,)]
+    p0 = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    hp = dict(lr=2e-2, num_data=20.0, momentum=0.8, temperature=1.0)
+    ch = O.Chain(p0, O.Group(**hp), dot_dtype=np.float64)
+    tc = OT.TorchVerletChain([torch.tensor(a) for a in p0], **hp)
+    z = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    O.sample_momentum(ch, lambda i, n: z[i].reshape(-1))
+    tc.sample_momentum(noise=[torch.tensor(a) for a in z])
+    for it in range(5):
+        gs = [rng.standard_normal(s).astype(np.float32) * 0.1 for s in shapes]
+        z = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+        for seg, g, tg in zip(ch.segs, gs, tc.g):
+            seg.g = g.reshape(-1).copy()
+            tg.copy_(torch.tensor(g))
+        O.verlet_step(ch, lambda i, n: z[i].reshape(-1), phase=O.PHASE_MID, calc_metrics=True)
+        tc.step(calc_metrics=True, noise=[torch.tensor(a) for a in z])
+        for i, seg in enumerate(ch.segs):
+            assert np.allclose(tc.p[i].numpy().reshape(-1), seg.p, rtol=1e-5, atol=1e-6)
+            assert np.allclose(tc.m[i].numpy().reshape(-1), seg.m, rtol=1e-5, atol=1e-6)
+            assert math.isclose(tc.delta_energy[i], seg.delta_energy, rel_tol=1e-4, abs_tol=1e-5)
+            assert math.isclose(tc.est_temperature[i], seg.est_temperature, rel_tol=1e-5)
