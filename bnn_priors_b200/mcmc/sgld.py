@@ -66,6 +66,15 @@ class SGLD(torch.optim.Optimizer):
         self.update_preconditioner()
         self._step_count = 0  # keep the `torch.optim.scheduler` happy
 
+    def add_param_group(self, param_group):
+        """Groups are laid out in HBM when the sampler is constructed (the reference's runners pass
+        all parameters to the constructor, inference.py:86-94); adding one later is refused rather
+        than silently ignored."""
+        if getattr(self, "_flat", None) is not None:
+            raise NotImplementedError("bnn_priors_b200 samplers lay their parameter groups out at construction; "
+                                      "pass every group to the constructor")
+        super().add_param_group(param_group)
+
     # ------------------------------------------------------------------ engine access
     @property
     def flat_groups(self):

@@ -431,6 +431,23 @@ def test_default_zero_grad_drops_gradients_and_step_copies_them_in():
     assert torch.equal(fg.G, fg.prev_g)
 
 
+def test_optimizer_protocol_state_dict_and_late_param_groups():
+    mcmc = _mcmc()
+    ps = _params(3, 50)
+    opt = mcmc.VerletSGLD(ps, lr=1e-2, num_data=10, momentum=0.9, temperature=1.0)
+    opt.sample_momentum()
+    for p in ps:
+        p.grad = torch.ones_like(p)
+    opt.initial_step(save_state=True)
+    sd = opt.state_dict()                                   # torch.optim.Optimizer protocol
+    assert len(sd["param_groups"]) == 1 and sd["param_groups"][0]["lr"] == 1e-2
+    assert len(sd["state"]) == 3
+    st = sd["state"][0]
+    assert torch.equal(st["momentum_buffer"], opt.state[ps[0]]["momentum_buffer"]) and "delta_energy" in st
+    with pytest.raises(NotImplementedError, match="at construction"):
+        opt.add_param_group(dict(params=_params(1, 5)))
+
+
 def test_two_param_groups():
     mcmc = _mcmc()
     a, b = _params(2, 3000), _params(2, 70)
