@@ -21,8 +21,14 @@
 // step never synchronises the host.
 //
 // The path is HBM-bound elementwise work: no tensor cores, no shared-memory tiles;
-// what matters is coalesced 16-byte accesses, enough loads in flight per SM and a
-// lean instruction stream for the Philox rounds.
+// what matters is coalesced 16-byte accesses, enough loads in flight per SM, a lean
+// instruction stream for the Philox rounds -- and, for chains larger than the 126 MB L2,
+// what consecutive launches leave each other there: they walk the chain in opposite
+// directions (BNNP_F_REVERSE) with evict-last P / M accesses.
+//
+// Also here: bnnp_prepass_kernel (the read-only pre-pass of the hierarchical priors,
+// BNNP_F_HYPER), bnnp_finalize_kernel, bnnp_rollback_kernel and the host-side layout
+// planner.  The evaluation kernels of include/bnnp_eval.h live in bnnp_eval.cu.
 
 #include "bnnp.h"
 

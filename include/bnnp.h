@@ -1,9 +1,11 @@
 /* bnnp.h -- C ABI of the B200 (sm_100a) SG-MCMC sampler kernels.
  *
  * This is the drop-in boundary for ONE path of ratschlab/bnn_priors: the inner
- * loop of bnn_priors/mcmc (SGLD, VerletSGLD, HMC) plus the elementwise
- * Normal / Laplace / Student-t prior gradient.  Each entry point names the
- * reference code it replaces (paths relative to the reference checkout).
+ * loop of bnn_priors/mcmc (SGLD, VerletSGLD, HMC) plus the gradient and log-density
+ * of the elementwise priors (Normal / Laplace / Student-t and the other closed forms
+ * of bnn_priors/prior, incl. sampled scales).  Each entry point names the reference
+ * code it replaces (paths relative to the reference checkout).  The per-epoch test
+ * evaluation has its own header, bnnp_eval.h.
  *
  * Conventions
  *  - plain C types only; every pointer inside BnnpLaunch is a DEVICE pointer
@@ -19,7 +21,7 @@
  * replay-noise array, all with the SAME layout: tensor t (a "segment") occupies
  * [off_t, off_t + numel_t), off_t a multiple of BNNP_SEG_ALIGN floats; the gap
  * up to the next segment is padding the kernels keep at zero.  A segment is cut
- * into chunks of BNNP_CHUNK floats; one CTA processes one chunk.
+ * into chunks of BNNP_CHUNK floats; one CTA processes one chunk (BnnpChunk).
  */
 #ifndef BNNP_H
 #define BNNP_H
