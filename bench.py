@@ -356,6 +356,15 @@ def run_gpu(args):
     h2d = 4 * fg.total
     d2h = fg.nseg * N.STATE_STRIDE * 8
 
+    # ---- cycle-end all-gather of the samples (one per cycle, outside the step loop)
+    gather_ms = None
+    if dist_on:
+        ring = CH.SampleRing(1, fg.total, device)
+        ring.push(fg.P, step=0)
+        ring.gather()
+        torch.cuda.synchronize(device)
+        gather_ms = timed_gpu(lambda: ring.gather(), 3, device, True) / 3
+
     # ---- other transitions of the path (kernel time, same chain size), for context
     extra = {}
     if rank == 0 and not args.no_extra:
@@ -376,14 +385,38 @@ def run_gpu(args):
             extra[name] = {"us_per_step": ms * 1e3, "param_updates_per_s": n / (ms * 1e-3),
                            "alg_GBs": ALG_BYTES_PER_PARAM * n / (ms * 1e-3) / 1e9}
 
-    # ---- cycle-end all-gather of the samples (one per cycle, outside the step loop)
-    gather_ms = None
-    if dist_on:
-        ring = CH.SampleRing(1, fg.total, device)
-        ring.push(fg.P, step=0)
-        ring.gather()
-        torch.cuda.synchronize(device)
-        gather_ms = timed_gpu(lambda: ring.gather(), 3, device, True) / 3
+        # hierarchical priors: every prior-carrying weight tensor gets a sampled scale;
+        # a step = read-only pre-pass + its epilogue + the step launch, timed through the API
+        try:
+            from bnn_priors_b200 import mcmc
+            del opt, params, fg
+            torch.cuda.empty_cache()
+            gen = torch.Generator(device=device).manual_seed(0)
+            params, links = [], []
+            for t in load_tensors():
+                params.append(torch.nn.Parameter(torch.randn(tuple(t["shape"]), device=device, generator=gen)
+                                                 * (t["scale"] if t["kind"] else 1.0)))
+                if t["kind"] and len(t["shape"]) > 1:
+                    links.append((len(params) - 1, len(params), t))
+                    params.append(torch.nn.Parameter(torch.tensor(0.1, device=device)))
+            opt = mcmc.VerletSGLD(params, **HP, seed=0)
+            (fg,) = opt.flat_groups
+            for w, h, t in links:
+                fg.set_prior(w, N.PRIOR_NORMAL, 0.0, t["scale"], 3.0)
+                fg.set_hyper_link(w, h, N.PRIOR_HYPER_GAMMA, 1.0, 1.0)
+            fg.prior_fused = True
+            for p, v in zip(params, fg.g_views):
+                p.grad = v
+                v.normal_(0.0, 1e-3, generator=gen)
+            opt.sample_momentum()
+            hstep = lambda: opt.step(calc_metrics=False)   # noqa: E731
+            for _ in range(5):
+                hstep()
+            ms = timed_gpu(hstep, min(K, 50), device, False) / min(K, 50)
+            extra[f"VerletSGLD.step+{len(links)}_sampled_scales(prepass+epilogue+step)"] = {
+                "us_per_step": ms * 1e3, "param_updates_per_s": n / (ms * 1e-3), "alg_GBs": ALG_BYTES_PER_PARAM * n / (ms * 1e-3) / 1e9}
+        except Exception as e:      # context only: never lose the headline because of it
+            extra["VerletSGLD.step+sampled_scales"] = {"error": repr(e)}
 
     # ---- CPU baseline beside it (rank 0, N == 1 only)
     cpu = None
@@ -477,6 +510,7 @@ def main():
     try:
         import torch.distributed as dist
         if dist.is_initialized():
+            dist.barrier()                  # rank 0 may still be timing the context cases
             dist.destroy_process_group()
     except Exception:
         pass
