@@ -46,6 +46,7 @@ F_PRIOR_GRAD = 1 << 12
 F_ALL_SUMS = 1 << 13
 F_HYPER = 1 << 14
 F_REVERSE = 1 << 15
+F_HYPER_POST = 1 << 16
 
 (S_DELTA_ENERGY, S_PREV_NEW_MOM, S_EST_MM, S_EST_PG, S_SUM_GG, S_SUM_MM, S_SQ_MEAN,
  S_LOG_PRIOR, S_GM_OLD, S_GM_NEW, S_MM_OLD, S_MM_NEW, S_NONFINITE, S_LAUNCHES, S_HYPER) = range(15)

@@ -437,6 +437,9 @@ __host__ __device__ inline int sums_needed(int op, uint32_t flags) {
 __device__ void hyper_epilogue(const BnnpLaunch& L, const BnnpEpilogue& E, const BnnpSegment& sd, double* st,
                                const double* r) {
     if (sd.link < 0 || sd.link >= L.nseg) return;
+    // BNNP_F_HYPER_POST: the launch was a step; r[BNNP_NRED] is the linked segment's sum of log-density
+    // terms at the parameters now in P, evaluated with the scale the table held during the launch
+    const bool post = (E.flags & BNNP_F_HYPER_POST) != 0;
     if (is_hyper_kind(sd.prior_kind)) {
         const BnnpSegment w = L.segs[sd.link];
         const double u = (double)L.P[sd.off];
@@ -454,15 +457,29 @@ __device__ void hyper_epilogue(const BnnpLaunch& L, const BnnpEpilogue& E, const
             lp = -0.4515827052894548 /* log(2/pi) */ - log(a) - log1p(q * q);
             dlp = -(2.0 * q / a) / (1.0 + q * q) * ds;
         }
-        const double T = r[BNNP_NRED], n = (double)w.numel, df = (double)w.prior_df;
+        const double n = (double)w.numel, df = (double)w.prior_df;
+        double T = r[BNNP_NRED];
+        if (post) {
+            const double s_old = (double)w.prior_scale;              // nobody else writes it
+            T = w.prior_kind == BNNP_PRIOR_NORMAL ? -2.0 * s_old * s_old * T : -s_old * T;
+        }
         double dl_ds = 0.0;                                          // sum_i d log p(w_i | s) / ds
         if (w.prior_kind == BNNP_PRIOR_NORMAL) dl_ds = T / (s * s * s) - n / s;
         else if (w.prior_kind == BNNP_PRIOR_LAPLACE) dl_ds = T / (s * s) - n / s;
         else if (w.prior_kind == BNNP_PRIOR_STUDENT_T) dl_ds = (df + 1.0) * T / s - n / s;
         st[BNNP_S_LOG_PRIOR] = lp;
         st[BNNP_S_HYPER] = -E.inv_num_data * (dl_ds * ds + dlp);
+        if (post) {
+            // the linked segment's log-prior at the new parameters AND the new scale
+            double* st_w = L.seg_state + (int64_t)sd.link * BNNP_STATE_STRIDE;
+            BnnpSegment now = w;
+            now.prior_scale = (float)s;
+            st_w[BNNP_S_LOG_PRIOR] = (w.prior_kind == BNNP_PRIOR_NORMAL ? -0.5 * T / (s * s) : -T / s) +
+                                     n * log_prior_const(now);
+            st_w[BNNP_S_HYPER] = T;
+        }
         L.segs[sd.link].prior_scale = (float)s;
-    } else if (may_have_hyper_scale(sd.prior_kind)) {
+    } else if (may_have_hyper_scale(sd.prior_kind) && !post) {
         const BnnpSegment h = L.segs[sd.link];
         double s, ds;
         hyper_scale(h, (double)L.P[h.off], s, ds);
@@ -521,7 +538,10 @@ __device__ void segment_epilogue(const BnnpEpilogue& E, double* seg_state, const
     }
     if (flags & BNNP_F_UPDATE_SQ)                                   // sgld.py:153-154, through its mean
         st[BNNP_S_SQ_MEAN] = E.rms_alpha * st[BNNP_S_SQ_MEAN] + (1.0 - E.rms_alpha) * (gg / (double)sd.numel);
-    if (flags & BNNP_F_LOG_PRIOR)
+    // (under BNNP_F_HYPER_POST the log-prior of a segment with a sampled scale is written by its hyper
+    // segment's epilogue, at the new scale)
+    if ((flags & BNNP_F_LOG_PRIOR) &&
+        !((flags & BNNP_F_HYPER_POST) && sd.link >= 0 && may_have_hyper_scale(sd.prior_kind)))
         st[BNNP_S_LOG_PRIOR] = r[R_LOGP] + (double)sd.numel * log_prior_const(sd);
     st[BNNP_S_LAUNCHES] += 1.0;
 }
@@ -554,18 +574,20 @@ __device__ void apply_pending(const BnnpLaunch& L, const BnnpSegment& sd, int se
         const double t = fold_records(L.partials + rec0 * BNNP_NRED + k, sd.num_chunks, lane);
         if (lane == 0) s_sum[k] = t;
     }
-    if ((E.flags & BNNP_F_HYPER) && is_hyper_kind(sd.prior_kind) && sd.link >= 0 && sd.link < L.nseg && warp == 0) {
+    if ((E.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)) && is_hyper_kind(sd.prior_kind) && sd.link >= 0 &&
+        sd.link < L.nseg && warp == 0) {
         // the statistic of the segment this hyper-parameter scales: fold that segment's records
         // here, so that no CTA depends on another CTA's epilogue
         const BnnpSegment w = L.segs[sd.link];
-        const double* base = L.partials + ((int64_t)E.parity * L.nchunks_total + w.first_chunk) * BNNP_NRED + R_GM_OLD;
+        const double* base = L.partials + ((int64_t)E.parity * L.nchunks_total + w.first_chunk) * BNNP_NRED +
+                             ((E.flags & BNNP_F_HYPER_POST) ? R_LOGP : R_GM_OLD);
         const double t = fold_records(base, w.num_chunks, lane);
         if (lane == 0) s_sum[BNNP_NRED] = t;
     }
     __syncthreads();
     if (tid == 0) {
         segment_epilogue(E, L.seg_state, sd, seg, s_sum);
-        if (E.flags & BNNP_F_HYPER) hyper_epilogue(L, E, sd, L.seg_state + (int64_t)seg * BNNP_STATE_STRIDE, s_sum);
+        if (E.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)) hyper_epilogue(L, E, sd, L.seg_state + (int64_t)seg * BNNP_STATE_STRIDE, s_sum);
     }
     __syncthreads();   // s_sum is reused by the caller
 }
@@ -990,9 +1012,15 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
     if (misaligned(a->P) || misaligned(a->G) || misaligned(a->M) || misaligned(a->prev_p) || misaligned(a->prev_g) ||
         misaligned(a->prev_m) || misaligned(a->replay_noise) || misaligned(a->chunks))
         return fail(BNNP_E_ALIGN, "bnnp_launch: flat arrays and the chunk table must be 16-byte aligned");
-    if (a->pending.valid && (a->pending.flags & BNNP_F_HYPER))
-        return fail(BNNP_E_ARG, "bnnp_launch: the epilogue of a BNNP_F_HYPER launch rewrites the segment table; "
-                                "bnnp_finalize first");
+    if (a->pending.valid && (a->pending.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)))
+        return fail(BNNP_E_ARG, "bnnp_launch: the epilogue of a BNNP_F_HYPER / BNNP_F_HYPER_POST launch rewrites the "
+                                "segment table; bnnp_finalize first");
+    if ((f & BNNP_F_HYPER_POST) &&
+        ((f & BNNP_F_HYPER) || a->chunk_ids != nullptr ||
+         (f & (BNNP_F_WRITE_P | BNNP_F_PRIOR_GRAD | BNNP_F_LOG_PRIOR)) !=
+             (BNNP_F_WRITE_P | BNNP_F_PRIOR_GRAD | BNNP_F_LOG_PRIOR)))
+        return fail(BNNP_E_ARG, "bnnp_launch: BNNP_F_HYPER_POST needs a step over all chunks with "
+                                "WRITE_P | PRIOR_GRAD | LOG_PRIOR");
     if ((f & BNNP_F_HYPER) &&
         (a->op != BNNP_OP_REDUCE || !(f & BNNP_F_LOG_PRIOR) || !(f & BNNP_F_READ_P) || a->chunk_ids != nullptr ||
          (f & ~(uint32_t)(BNNP_F_HYPER | BNNP_F_LOG_PRIOR | BNNP_F_READ_P | BNNP_F_REVERSE))))
@@ -1020,8 +1048,8 @@ int bnnp_finalize(const BnnpLaunch* a, void* stream) {
     if (!a->pending.valid) return 0;
     if (a->nseg <= 0 || a->segs == nullptr || a->seg_state == nullptr || a->partials == nullptr || a->stamps == nullptr)
         return fail(BNNP_E_ARG, "bnnp_finalize: null table pointer");
-    if ((a->pending.flags & BNNP_F_HYPER) && a->P == nullptr)
-        return fail(BNNP_E_ARG, "bnnp_finalize: the epilogue of a BNNP_F_HYPER launch reads P");
+    if ((a->pending.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)) && a->P == nullptr)
+        return fail(BNNP_E_ARG, "bnnp_finalize: the epilogue of a BNNP_F_HYPER / BNNP_F_HYPER_POST launch reads P");
     if ((a->pending.parity | 1) != 1) return fail(BNNP_E_ARG, "bnnp_finalize: parity must be 0 or 1");
     bnnp_finalize_kernel<<<a->nseg, THREADS, 0, (cudaStream_t)stream>>>(*a);
     cudaError_t e = cudaGetLastError();

@@ -381,6 +381,32 @@ class FlatGroup:
     def has_hyper(self) -> bool:
         return bool(self.hyper_links)
 
+    @property
+    def hyper_post_ok(self) -> bool:
+        """All sampled scales belong to Normal / Laplace segments: a step can refresh the scales,
+        hyper gradients and log-priors for the parameters it leaves behind (BNNP_F_HYPER_POST),
+        so the next step needs no pre-pass."""
+        k = self.table["prior_kind"]
+        return bool(self.hyper_links) and all(int(k[w]) in (N.PRIOR_NORMAL, N.PRIOR_LAPLACE)
+                                              for w in self.hyper_links.values())
+
+    def step_prior_flags(self, prior_flags: int, chunks) -> int:
+        "LOG_PRIOR (and HYPER_POST) for a step launch that writes P, given the flags of _prior_flags"
+        if not prior_flags:
+            return 0
+        if not self.hyper_links:
+            return N.F_LOG_PRIOR
+        if chunks is None and self.hyper_post_ok:
+            return N.F_LOG_PRIOR | N.F_HYPER_POST
+        return 0
+
+    def after_hyper_post(self) -> None:
+        """The epilogue of a BNNP_F_HYPER_POST step rewrites the segment table: apply it now; then
+        scales, hyper gradients and log-priors describe the parameters the step left in P."""
+        self.flush_pending()
+        self._hyper_valid = self._lp_valid = True
+        self._hyper_pversion = self._lp_pversion = self._p_version()
+
     def hyper_fresh(self) -> bool:
         return self._hyper_valid and not self._table_dirty and self._hyper_pversion == self._p_version()
 

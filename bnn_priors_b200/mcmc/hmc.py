@@ -65,8 +65,7 @@ class HMC(VerletSGLD):
             flags |= N.F_SAVE_STATE
         if not is_final:
             flags |= N.F_WRITE_P | N.F_UPDATE_SQ
-            if pf and not fg.has_hyper:
-                flags |= N.F_LOG_PRIOR
+            flags |= fg.step_prior_flags(pf, chunks)
         fg.launch(self._OP, self._phase(is_initial, is_final), flags, N.NOISE_NONE,
                   cm=1.0, cg=-.5 * group['grad_v'] * group['bhn'], cn=0.0, cp=group['bh'],
                   inv_num_data=inv_n, rms_alpha=group['rmsprop_alpha'], chunks=chunks)
@@ -76,3 +75,5 @@ class HMC(VerletSGLD):
         if is_initial:
             fg.have_delta = True
         fg.note_step_sums(flags, self._OP)
+        if flags & N.F_HYPER_POST:
+            fg.after_hyper_post()

@@ -232,8 +232,7 @@ class SGLD(torch.optim.Optimizer):
             flags |= N.F_WRITE_P | N.F_UPDATE_SQ
             if a > 0:
                 flags |= N.F_WRITE_M
-            if pf and not fg.has_hyper:
-                flags |= N.F_LOG_PRIOR
+            flags |= fg.step_prior_flags(pf, chunks)
             noise = fg.take_noise_mode(group['temperature'] > 0)
             fg.launch(self._OP, N.PHASE_MID, flags, noise,
                       cm=a, cg=-group['hn'], cn=group['noise_std'], cp=group['h'],
@@ -244,6 +243,8 @@ class SGLD(torch.optim.Optimizer):
             fg.have_metrics = True
             fg.metrics_num_data = group['num_data']
         fg.note_step_sums(flags, self._OP)
+        if flags & N.F_HYPER_POST:
+            fg.after_hyper_post()
 
     # ------------------------------------------------------------------ preconditioner
     @torch.no_grad()

@@ -154,8 +154,7 @@ class VerletSGLD(SGLD):
             flags |= N.F_SAVE_STATE
         if not is_final:
             flags |= N.F_WRITE_P | N.F_UPDATE_SQ
-            if pf and not fg.has_hyper:
-                flags |= N.F_LOG_PRIOR
+            flags |= fg.step_prior_flags(pf, chunks)
         # the reference draws randn_like(p) even when noise_std == 0 (:163); a replayed
         # trace carries that draw, the Philox stream simply skips it
         noise = fg.take_noise_mode(True)
@@ -175,3 +174,5 @@ class VerletSGLD(SGLD):
         if is_initial:
             fg.have_delta = True
         fg.note_step_sums(flags, self._OP)
+        if flags & N.F_HYPER_POST:
+            fg.after_hyper_post()

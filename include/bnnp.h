@@ -117,6 +117,16 @@ enum {
                                        (HMC initial/final need m.m: hmc.py:50-53,32-33);
                                        otherwise a launch only reduces what its epilogue
                                        reads: g.g always, g.m and g.m' for VERLET       */
+    BNNP_F_HYPER_POST = 1u << 16,   /* a step launch (WRITE_P | PRIOR_GRAD | LOG_PRIOR, all chunks)
+                                       of a chain whose sampled scales all belong to NORMAL /
+                                       LAPLACE segments: its epilogue -- to be applied with
+                                       bnnp_finalize before the next launch -- does what the
+                                       BNNP_F_HYPER pre-pass would do for the parameters this
+                                       launch leaves in P, because for those two densities the
+                                       statistic of d log p / d scale follows from the sum of
+                                       log-density terms the launch reduces anyway (sum d^2 =
+                                       -2 s^2 sum(-z^2/2), sum |d| = -s sum(-|z|)).  Saves the
+                                       pre-pass of the NEXT step.                          */
     BNNP_F_REVERSE = 1u << 15,      /* CTA i processes chunk nchunks-1-i.  A chain larger than
                                        L2 that alternates the direction from launch to launch
                                        starts each launch on the lines the previous one

@@ -55,20 +55,36 @@ def test_kernel_matches_reference_log_prob_and_gradients(case):
     table = np.frombuffer(fg.table_dev.cpu().numpy().tobytes(), dtype=N.SEGMENT_DTYPE)
     assert math.isclose(float(table["prior_scale"][1]), case["scale"], rel_tol=2e-6)
     # gradient through a step: lr = N = 1, no momentum, no noise, zero likelihood gradient => x' = x + dlogp/dx
+    post = case["kind"] in (N.PRIOR_NORMAL, N.PRIOR_LAPLACE)          # the step refreshes the hyper state itself
+    assert fg.hyper_post_ok == post
     launches = fg.launches
     opt.step(calc_metrics=False)
-    assert fg.launches == launches + 1                                  # the pre-pass was fresh: one launch
-    assert not fg.hyper_fresh()
+    # the pre-pass was fresh: one launch (+ the epilogue launch of BNNP_F_HYPER_POST)
+    assert fg.launches == launches + (2 if post else 1)
+    assert fg.hyper_fresh() == post
     moved = params[1].detach().cpu().numpy().astype(np.float64) - p_ref.astype(np.float64)
     tol = 2e-5 * np.abs(g_ref) + 2.5e-7 * np.maximum(np.abs(p_ref), np.abs(p_ref + g_ref)) + 1e-30
     assert np.all(np.abs(moved - g_ref) <= tol), float(np.max(np.abs(moved - g_ref) / tol))
     du = float(params[2].detach().double()) - float(np.float32(case["u"]))
     assert abs(du - case["grad_u"]) <= 2e-5 * abs(case["grad_u"]) + 2.5e-7 * max(abs(case["u"]), abs(case["u"] + case["grad_u"]))
     assert float(fg.fetch()[1, N.S_NONFINITE]) == 0.0
-    # a second step needs a new pre-pass (the hyper-parameter moved): pre-pass + epilogue + step
+    if post:
+        # what the step's epilogue left for the NEW parameters == what a pre-pass computes for them
+        after = fg.fetch().copy()
+        scale_after = float(np.frombuffer(fg.table_dev.cpu().numpy().tobytes(), dtype=N.SEGMENT_DTYPE)["prior_scale"][1])
+        fg.hyper_prepass(1.0)
+        again = fg.fetch()
+        scale_again = float(np.frombuffer(fg.table_dev.cpu().numpy().tobytes(), dtype=N.SEGMENT_DTYPE)["prior_scale"][1])
+        u_now = float(params[2].detach())
+        if math.isfinite(u_now) and np.isfinite(again[:3, N.S_LOG_PRIOR]).all():
+            assert scale_after == scale_again
+            for row, col in ((1, N.S_LOG_PRIOR), (2, N.S_LOG_PRIOR), (2, N.S_HYPER), (1, N.S_HYPER)):
+                assert math.isclose(after[row, col], again[row, col], rel_tol=2e-5, abs_tol=1e-6), (row, col, after[row, col], again[row, col])
+    # a second step: pre-pass + epilogue + step where the scale statistic needs the new scale (StudentT),
+    # step + epilogue otherwise
     launches = fg.launches
     opt.step(calc_metrics=False)
-    assert fg.launches == launches + 3
+    assert fg.launches == launches + (2 if post else 3)
 
 
 CASES = [(LM.Normal, "gamma", {}), (LM.Normal, "uniform", {}), (LM.Normal, "horseshoe", dict(hyperscale=2.0)),
