@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BNNP_ABI_VERSION 7
+#define BNNP_ABI_VERSION 8
 
 #define BNNP_SEG_ALIGN 32      /* floats: every segment starts on a 128-byte line */
 #ifndef BNNP_THREADS
