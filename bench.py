@@ -385,8 +385,9 @@ def run_gpu(args):
             extra[name] = {"us_per_step": ms * 1e3, "param_updates_per_s": n / (ms * 1e-3),
                            "alg_GBs": ALG_BYTES_PER_PARAM * n / (ms * 1e-3) / 1e9}
 
-        # hierarchical priors: every prior-carrying weight tensor gets a sampled scale;
-        # a step = read-only pre-pass + its epilogue + the step launch, timed through the API
+        # hierarchical priors: every prior-carrying weight tensor gets a sampled scale
+        # (NormalGamma); a step = the step launch + its epilogue launch (BNNP_F_HYPER_POST), timed
+        # through the API
         try:
             from bnn_priors_b200 import mcmc
             del opt, params, fg
@@ -413,7 +414,7 @@ def run_gpu(args):
             for _ in range(5):
                 hstep()
             ms = timed_gpu(hstep, min(K, 50), device, False) / min(K, 50)
-            extra[f"VerletSGLD.step+{len(links)}_sampled_scales(prepass+epilogue+step)"] = {
+            extra[f"VerletSGLD.step+{len(links)}_sampled_scales(step+epilogue_launch)"] = {
                 "us_per_step": ms * 1e3, "param_updates_per_s": n / (ms * 1e-3), "alg_GBs": ALG_BYTES_PER_PARAM * n / (ms * 1e-3) / 1e9}
         except Exception as e:      # context only: never lose the headline because of it
             extra["VerletSGLD.step+sampled_scales"] = {"error": repr(e)}

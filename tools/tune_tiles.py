@@ -68,6 +68,16 @@ if not only or "verlet_hier" in only.split(","):
     out["hier_prepass_plus_epilogue"] = [round(ms[0] * 1e3, 2), round(ms[2] * 1e3, 2)]
     del opt, params, fg
     torch.cuda.empty_cache()
+if not only or "rollback" in only.split(","):
+    # the restore after a rejected proposal (verlet_sgld.py:63-69): P, G, M <- prev_*  (24 B/param)
+    opt, params, fg = bench.make_chain(dev, 0, "VerletSGLD")
+    opt.initial_step(save_state=True, calc_metrics=False)
+    for _ in range(20):
+        fg.rollback()
+    ms = sorted(bench.timed_gpu(fg.rollback, K, dev, False) / K for _ in range(5))
+    out["rollback"] = [round(ms[0] * 1e3, 2), round(ms[2] * 1e3, 2)]
+    del opt, params, fg
+    torch.cuda.empty_cache()
 if not only or "probe" in only.split(","):
     # ceiling of the access pattern: read p, g, m / write p, m and nothing else
     from bnn_priors_b200 import _native as N
