@@ -214,7 +214,7 @@ class FlatGroup:
         self.serpentine = os.environ.get("BNNP_SERPENTINE", "1") != "0"
         self.seg_states = [SegState(self, i) for i in range(self.nseg)]
         self._sync_rows = list(zip(self.params, self.g_views, self.p_views, self._p_ptrs))
-        self._g_seen: List[Optional[tuple]] = [None] * self.nseg     # (weakref to the foreign grad tensor, its version) last copied into G
+        self._g_seen: List[Optional[tuple]] = [None] * self.nseg     # per tensor: (weakref to the foreign grad tensor, its version) last copied into G, or "zero"
         self.args = N.BnnpLaunch()
         self.launches = 0
 
@@ -248,9 +248,12 @@ class FlatGroup:
             if g is not gv:
                 if g is None and i in self.hyper_links:
                     # a fused hyper-parameter reaches the loss only through the prior, which is no
-                    # longer in autograd: its likelihood gradient is zero
-                    gv.zero_()
-                    p.grad = gv
+                    # longer in autograd: its likelihood gradient is zero.  Its slot of G is zeroed
+                    # once and stays zero as long as nobody hands a gradient over (no launch, no
+                    # re-binding per step)
+                    if self._g_seen[i] != "zero":
+                        gv.zero_()
+                        self._g_seen[i] = "zero"
                 elif g is None:
                     if raise_on_no_grad:
                         raise RuntimeError(f"No gradient for parameter with shape {p.shape}")
@@ -263,7 +266,7 @@ class FlatGroup:
                     # once P has moved: the reference's p.grad holds the prior gradient at the OLD p)
                     seen = self._g_seen[i]
                     ver = g._version
-                    if seen is None or seen[0]() is not g or seen[1] != ver:
+                    if seen is None or seen == "zero" or seen[0]() is not g or seen[1] != ver:
                         dst.append(gv)
                         src.append(g)
                         self._g_seen[i] = (weakref.ref(g), ver)    # weak: the old gradient may be freed
