@@ -273,7 +273,7 @@ class FlatGroup:
             if p.data_ptr() != ptr:
                 pv.copy_(p.data)
                 p.data = pv
-                self._lp_valid = False
+                self._lp_valid = self._hyper_valid = False
             i += 1
         if dst:
             try:
