@@ -38,15 +38,37 @@ def up_to_date() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libbnnp.so.  bnnp_kernels.cu is compiled as three translation units in parallel
+    (-DBNNP_PART=0/1/2: the step-kernel instantiations of one noise kind each) next to bnnp_eval.cu,
+    then linked: about a third of the time of a single nvcc call."""
     if not force and up_to_date():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", OUT] + SRC
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if r.returncode != 0:
+    objdir = os.path.join(os.path.dirname(OUT), "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = find_nvcc()
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE]
+    jobs = []
+    for part in (0, 1, 2):
+        obj = os.path.join(objdir, f"bnnp_kernels_part{part}.o")
+        jobs.append((obj, [nvcc] + compile_flags + [f"-DBNNP_PART={part}", "-c", SRC[0], "-o", obj]))
+    obj = os.path.join(objdir, "bnnp_eval.o")
+    jobs.append((obj, [nvcc] + compile_flags + ["-c", SRC[1], "-o", obj]))
+    procs = [(cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for _, cmd in jobs]
+    failed = False
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + out)
+        failed |= p.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed building libbnnp.so")
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + [o for o, _ in jobs]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(" ".join(link) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed linking libbnnp.so")
     return OUT
 
 

@@ -921,11 +921,42 @@ StepKernel pick_noise(bool prior, bool noise_first, int sums) {
     return noise_first ? pick_sums<NOISE, false, true>(sums) : pick_sums<NOISE, false, false>(sums);
 }
 
+}  // namespace
+
+// The 36 instantiations of the step kernel take most of the build time, so the file can be compiled
+// as three translation units in parallel (bnn_priors_b200/build.py): -DBNNP_PART=0 / 1 / 2 keeps the
+// instantiations of one noise kind each (part 0 also holds the API); without BNNP_PART everything is
+// in one unit.  The entry points below have external linkage and return the kernel as void*.
+#ifndef BNNP_PART
+#define BNNP_PART -1
+#endif
+void* bnnp_pick_noise_none(bool prior, bool noise_first, int sums);
+void* bnnp_pick_noise_replay(bool prior, bool noise_first, int sums);
+void* bnnp_pick_noise_philox(bool prior, bool noise_first, int sums);
+#if BNNP_PART == -1 || BNNP_PART == 0
+void* bnnp_pick_noise_none(bool prior, bool noise_first, int sums) {
+    return (void*)pick_noise<BNNP_NOISE_NONE>(prior, noise_first, sums);
+}
+#endif
+#if BNNP_PART == -1 || BNNP_PART == 1
+void* bnnp_pick_noise_replay(bool prior, bool noise_first, int sums) {
+    return (void*)pick_noise<BNNP_NOISE_REPLAY>(prior, noise_first, sums);
+}
+#endif
+#if BNNP_PART == -1 || BNNP_PART == 2
+void* bnnp_pick_noise_philox(bool prior, bool noise_first, int sums) {
+    return (void*)pick_noise<BNNP_NOISE_PHILOX>(prior, noise_first, sums);
+}
+#endif
+
+#if BNNP_PART == -1 || BNNP_PART == 0
+namespace {
+
 StepKernel pick_kernel(int noise, bool prior, bool noise_first, int sums) {
     switch (noise) {
-        case BNNP_NOISE_NONE: return pick_noise<BNNP_NOISE_NONE>(prior, noise_first, sums);
-        case BNNP_NOISE_REPLAY: return pick_noise<BNNP_NOISE_REPLAY>(prior, noise_first, sums);
-        case BNNP_NOISE_PHILOX: return pick_noise<BNNP_NOISE_PHILOX>(prior, noise_first, sums);
+        case BNNP_NOISE_NONE: return (StepKernel)bnnp_pick_noise_none(prior, noise_first, sums);
+        case BNNP_NOISE_REPLAY: return (StepKernel)bnnp_pick_noise_replay(prior, noise_first, sums);
+        case BNNP_NOISE_PHILOX: return (StepKernel)bnnp_pick_noise_philox(prior, noise_first, sums);
     }
     return nullptr;
 }
@@ -1088,3 +1119,4 @@ int bnnp_rollback(float* P, float* G, float* M, const float* prev_p, const float
 }
 
 }  // extern "C"
+#endif  // BNNP_PART == -1 || BNNP_PART == 0
