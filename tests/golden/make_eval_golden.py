@@ -83,5 +83,39 @@ def main():
     np.savez_compressed(os.path.join(HERE, "eval.npz"), **out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not os.environ.get("CALIBRATION"):
     main()
+
+
+def calibration_case():
+    """Second fixture (tests/golden/eval_calibration.npz): the same classification case evaluated by the
+    reference with calibration_eval=True -- ensemble probabilities (recomputed like exp_utils.py:309-324)
+    and the ece / ace / rmsce values of the reference's third_party/calibration_error.py."""
+    torch.manual_seed(7)
+    x = torch.rand(N, 20)
+    y = torch.randint(0, 7, (N,))
+    y[:7] = torch.arange(7)
+    model = ClassificationDenseNet(20, 7, 16, depth=3, softmax_temp=1.0)
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=BATCH, shuffle=False)
+    samples = {}
+    for e in range(E):
+        model.sample_all_priors()
+        for k, v in model.state_dict().items():
+            samples.setdefault(k, []).append(v.detach().clone())
+    samples = {k: torch.stack(v) for k, v in samples.items()}
+    res = exp_utils.evaluate_model(model, loader, samples, likelihood_eval=True, accuracy_eval=True,
+                                   calibration_eval=True)
+    acc = []
+    with torch.no_grad():
+        for e in range(E):
+            model.load_state_dict({k: v[e] for k, v in samples.items()})
+            acc.append(torch.cat([model(bx).logits for bx, _ in loader]))
+    acc = torch.stack(acc).double()
+    ens = torch.distributions.Categorical(logits=acc.logsumexp(0) - np.log(E))
+    np.savez_compressed(os.path.join(HERE, "eval_calibration.npz"), acc_data=acc.float().numpy(), y=y.numpy(),
+                        probs_mean=ens.probs.numpy(), results=np.array(json.dumps(res)))
+    print("calibration", res)
+
+
+if __name__ == "__main__" and os.environ.get("CALIBRATION"):
+    calibration_case()

@@ -204,3 +204,29 @@ def test_torch_op_verlet_restatement_agrees_with_the_numpy_oracle():
             assert np.allclose(tc.m[i].numpy().reshape(-1), seg.m, rtol=1e-5, atol=1e-6)
             assert math.isclose(tc.delta_energy[i], seg.delta_energy, rel_tol=1e-4, abs_tol=1e-5)
             assert math.isclose(tc.est_temperature[i], seg.est_temperature, rel_tol=1e-5)
+
+
+def test_eval_oracle_ensemble_probabilities_and_calibration_inputs():
+    """tests/golden/eval_calibration.npz: the reference's evaluate_model with calibration_eval=True.  The
+    ensemble probabilities the evaluation hands to the calibration metrics (exp_utils.py:324-327) must be
+    the reference's; with the reference checkout present, its own ece / ace / rmsce on OUR probabilities
+    must give the recorded values."""
+    from oracle import eval_oracle as EO
+    z = np.load(os.path.join(GOLDEN_DIR, "eval_calibration.npz"))
+    want = json.loads(str(z["results"]))
+    acc = z["acc_data"]
+    labels = z["y"]
+    lps = np.take_along_axis(acc, labels[None, :, None].repeat(acc.shape[0], 0), 2)[..., 0]
+    got = EO.evaluate(acc, lps, labels, EO.CATEGORICAL)
+    assert np.allclose(got["probs_mean"], z["probs_mean"], rtol=1e-12, atol=1e-15)
+    assert math.isclose(got["lp_ensemble"], want["lp_ensemble"], rel_tol=1e-7)
+    if os.path.isdir("/root/reference/bnn_priors"):
+        import sys
+        sys.path.insert(0, "/root/reference")
+        try:
+            from bnn_priors.third_party.calibration_error import ace, ece, rmsce
+        finally:
+            sys.path.remove("/root/reference")
+        assert math.isclose(float(ece(labels, got["probs_mean"]).mean()), want["ece"], rel_tol=1e-9)
+        assert math.isclose(float(ace(labels, got["probs_mean"]).mean()), want["ace"], rel_tol=1e-9)
+        assert math.isclose(float(rmsce(labels, got["probs_mean"]).mean()), want["rmsce"], rel_tol=1e-9)
