@@ -18,16 +18,11 @@ from .verlet_sgld import VerletSGLD
 
 
 class HMC(VerletSGLD):
-    """HMC with Verlet integration.
+    """Hamiltonian Monte Carlo with the leapfrog integrator: GGMC at momentum 1 and temperature 1.
 
-    Args (identical to the reference, mcmc/hmc.py:25-27):
-        params (iterable): iterable of parameters to optimize or dicts defining
-            parameter groups
-        lr (float): learning rate
-        num_data (int): the number of data points in this learning task
-        raise_on_no_grad (bool): whether to complain if a parameter does not
-                                 have a gradient
-        raise_on_nan: whether to complain if a gradient is not all finite.
+    Constructor arguments: the reference's (mcmc/hmc.py:25-27) -- params, lr, num_data as for
+    `SGLD`; raise_on_no_grad; raise_on_nan (default True here: a trajectory with a non-finite
+    gradient is useless).
     """
     _OP = N.OP_HMC
 

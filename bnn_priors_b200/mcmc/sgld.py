@@ -23,21 +23,19 @@ def dot(a, b):
 
 
 class SGLD(torch.optim.Optimizer):
-    """SGLD with momentum, preconditioning and diagnostics from Wenzel et al. 2020.
+    """Stochastic-gradient Langevin dynamics with momentum (SGHMC), a per-tensor RMSProp
+    preconditioner and the kinetic / configurational temperature diagnostics of Wenzel et al. 2020.
 
-    Args (identical to the reference, mcmc/sgld.py:31-34):
-        params (iterable): iterable of parameters to optimize or dicts defining
-            parameter groups
-        lr (float): learning rate
-        num_data (int): the number of data points in this learning task
-        momentum (float): momentum factor (default: 0)
-        temperature (float): Temperature for tempering the posterior.
-                             temperature=0 corresponds to SGD with momentum.
-        rmsprop_alpha: decay for the moving average of the squared gradients
-        rmsprop_eps: the regularizer parameter for the RMSProp update
-        raise_on_no_grad (bool): whether to complain if a parameter does not
-                                 have a gradient
-        raise_on_nan: whether to complain if a gradient is not all finite.
+    Constructor arguments: the reference's, in the reference's order (mcmc/sgld.py:31-34) --
+        params            parameters, or dicts that define parameter groups
+        lr                step size (rescaled by num_data inside: h = sqrt(lr / N), hn = sqrt(lr N))
+        num_data          N, the size of the training set the minibatch gradients are averages over
+        momentum          a in [0, 1): 0 gives plain SGLD (no momentum buffer is kept)
+        temperature       T of the tempered posterior; 0 turns the sampler into SGD with momentum
+        rmsprop_alpha     decay of the running mean of the squared gradients
+        rmsprop_eps       regulariser added to that mean when the preconditioner is formed
+        raise_on_no_grad  a parameter without gradient is an error (else it is skipped)
+        raise_on_nan      a non-finite gradient raises ValueError
 
     Engine-only extras (keyword-only, not in the reference): `seed` / `chain` pick
     the Philox stream of the in-kernel noise (default: torch.initial_seed(), 0).
@@ -121,7 +119,7 @@ class SGLD(torch.optim.Optimizer):
     # ------------------------------------------------------------------ sample_momentum
     @torch.no_grad()
     def sample_momentum(self, keep=0.0):
-        "Sample the momenta for all the parameters  (mcmc/sgld.py:57-69)"
+        "Refresh the momentum of every tensor: m <- sqrt(keep) m + sqrt(T (1 - keep)) eps  (mcmc/sgld.py:57-69)"
         assert 0 <= keep and keep <= 1.
         if keep == 1.:
             return
@@ -205,8 +203,8 @@ class SGLD(torch.optim.Optimizer):
         return f, 1.0 / group['num_data']
 
     def _step_fn(self, group, fg: FlatGroup, chunks, calc_metrics=True, is_final=False):
-        """One SGLD transition of a whole group (mcmc/sgld.py:119-154).
-        if is_final, do not change parameters or momentum"""
+        """One SGLD transition of a whole group (mcmc/sgld.py:119-154); a final step only produces
+        the diagnostics and leaves parameters and momentum alone."""
         a = group['momentum']
         pf, inv_n = self._prior_flags(fg, group)
         flags = N.F_READ_P | N.F_READ_G | pf
@@ -249,10 +247,10 @@ class SGLD(torch.optim.Optimizer):
     # ------------------------------------------------------------------ preconditioner
     @torch.no_grad()
     def update_preconditioner(self):
-        """Updates the preconditioner for each parameter `state['preconditioner']` using
-        the estimated `state['square_avg']`  (mcmc/sgld.py:156-179).  The engine
-        keeps mean(square_avg) per tensor on the device -- the only way square_avg
-        is ever consumed -- so this is one small D2H copy."""
+        """Recompute every tensor's `state['preconditioner']` from the running mean of its squared
+        gradients: M_t = ((mean_t + eps) / min_t' (mean_t' + eps)) ** (-1/4)  (mcmc/sgld.py:156-179).
+        The engine keeps mean(square_avg) per tensor on the device -- square_avg is never consumed
+        in any other way -- so this is one small D2H copy."""
         precond = OrderedDict()
         min_s = math.inf
 
@@ -264,6 +262,5 @@ class SGLD(torch.optim.Optimizer):
                 min_s = min(min_s, precond[p])
 
         for p, new_M in precond.items():
-            # ^(1/2) to form the preconditioner,
-            # ^(-1/2) because we want the preconditioner's inverse square root.
+            # the sampler uses M^(-1/2) with M = sqrt(mean / min mean): one exponent of -1/4
             self.state[p]['preconditioner'] = (new_M / min_s)**(-1 / 4)
