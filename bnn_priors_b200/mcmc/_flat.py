@@ -199,6 +199,7 @@ class FlatGroup:
         # fused prior (prior_fusion.py)
         self.prior_fused = False
         self.grad_max: Optional[float] = None
+        self.clamp_armed = True       # prior_fusion.FusedPrior.arm_clamp
         self._lp_valid = False
         self._lp_pversion = None
         # hierarchical priors: {hyper segment: weight segment}; see hyper_prepass
@@ -379,6 +380,11 @@ class FlatGroup:
         self.hyper_links = {}
         self._table_dirty = True
         self._lp_valid = self._hyper_valid = False
+
+    @property
+    def clamp_active(self) -> bool:
+        "the fused step clamps g + prior gradient to +-grad_max (inference.py:219-220)"
+        return self.grad_max is not None and self.clamp_armed
 
     @property
     def has_hyper(self) -> bool:
@@ -623,7 +629,7 @@ class FlatGroup:
                     self.hyper_prepass(inv_num_data)
             else:
                 flags |= N.F_LOG_PRIOR
-            if self.grad_max is not None:
+            if self.clamp_active:
                 flags |= N.F_CLAMP_GRAD
         self.launch(N.OP_REDUCE, N.PHASE_MID, flags, N.NOISE_NONE, cm=1.0, inv_num_data=inv_num_data)
         self._gg_version = self.G._version

@@ -194,7 +194,7 @@ class SGLD(torch.optim.Optimizer):
         if not fg.prior_fused:
             return 0, 0.0
         f = N.F_PRIOR_GRAD
-        if fg.grad_max is not None:
+        if fg.clamp_active:
             f |= N.F_CLAMP_GRAD
         if fg.has_hyper and not fg.hyper_fresh():
             # hierarchical priors: current scales and -(1/N) dlog p/du come from a read-only

@@ -280,8 +280,11 @@ class _EngineValue(torch.autograd.Function):
 class FusedPrior:
     """Handle returned by `fuse_prior`; `.unfuse()` restores the model."""
 
-    def __init__(self, model, sampler, grad_max: Optional[float], verify: bool = True):
+    def __init__(self, model, sampler, grad_max: Optional[float], verify: bool = True, clamp: str = "always"):
+        if clamp not in ("always", "armed"):
+            raise ValueError("clamp must be 'always' or 'armed'")
         self.model, self.sampler = model, sampler
+        self.clamp_mode = clamp
         self.fused_modules: List[torch.nn.Module] = []
         self.other_modules: List[torch.nn.Module] = []
         self._had_attr = "log_prior" in model.__dict__
@@ -322,6 +325,7 @@ class FusedPrior:
             fg = sampler.flat_groups[gi]
             fg.prior_fused = True
             fg.grad_max = None if grad_max is None else float(grad_max)
+            fg.clamp_armed = clamp == "always"
             fg.invalidate_sums()
         dev = sampler.flat_groups[0].device
         self._anchor = torch.zeros((), device=dev, requires_grad=True)
@@ -349,6 +353,18 @@ class FusedPrior:
             lp = lp + m.log_prob()
         return lp
 
+    def arm_clamp(self, on: bool) -> None:
+        """clamp="armed": whether the +-grad_max clamp applies to the gradient now in p.grad.  The
+        overlay arms it for minibatch gradients (the runner clamps those, inference.py:219-220) and
+        disarms it for the full-data gradient (inference_reject.py:18-33 does not clamp)."""
+        if self.clamp_mode != "armed":
+            return
+        for gi in self.groups:
+            fg = self.sampler.flat_groups[gi]
+            if fg.clamp_armed != bool(on):
+                fg.clamp_armed = bool(on)
+                fg.invalidate_sums()
+
     def unfuse(self) -> None:
         for gi in self.groups:
             fg = self.sampler.flat_groups[gi]
@@ -357,6 +373,7 @@ class FusedPrior:
             fg.clear_hyper_links()
             fg.prior_fused = False
             fg.grad_max = None
+            fg.clamp_armed = True
             fg.invalidate_sums()
         if self._had_attr:
             self.model.log_prior = self._old_attr
@@ -364,9 +381,14 @@ class FusedPrior:
             del self.model.__dict__["log_prior"]
 
 
-def fuse_prior(model: torch.nn.Module, sampler, grad_max: Optional[float] = None, verify: bool = True) -> FusedPrior:
+def fuse_prior(model: torch.nn.Module, sampler, grad_max: Optional[float] = None, verify: bool = True,
+               clamp: str = "always") -> FusedPrior:
     """Move the supported priors of `model` from autograd into `sampler`'s kernel.
-    `grad_max` is the runner's gradient clamp (inference.py:219-220, default 1e6
-    in experiments/train_bnn.py:84): the reference clamps likelihood + prior
-    gradient together, so the kernel re-applies it to the fused sum."""
-    return FusedPrior(model, sampler, grad_max, verify)
+    `grad_max` is the runner's gradient clamp (inference.py:219-220, default 1e6 in
+    inference.py:13): the reference clamps likelihood + prior gradient together, so the kernel
+    applies it to the fused sum.  With an unchanged runner that still clamps p.grad (now the
+    likelihood part alone) first, the two differ when |likelihood gradient| > grad_max; the
+    overlay (`overlay.install(fuse_prior=True)`) removes the runner-side clamp and uses
+    clamp="armed" -- the kernel clamps only gradients the runner would have clamped -- which is
+    the reference's arithmetic exactly."""
+    return FusedPrior(model, sampler, grad_max, verify, clamp)
