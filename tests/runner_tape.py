@@ -105,6 +105,11 @@ def recording_class(base, tape: Tape, prior_grad_fn=None):
             ev = dict(op=op, kwargs=dict(kwargs), group={k: float(g0[k]) for k in GROUP_KEYS if k in g0})
             if op in STEP_OPS:
                 ev["grads"] = [None if p.grad is None else p.grad.detach().clone() for p in params]
+                # sum |p_i g_i| per tensor: the size of the terms dot(p, g) adds up (est_config_temp, sgld.py:146)
+                with torch.no_grad():
+                    ev["pg_abs"] = torch.stack([(p.detach() * p.grad).abs().sum().double() if p.grad is not None
+                                                else torch.zeros((), dtype=torch.float64, device=p.device)
+                                                for p in params]).tolist()
                 if prior_grad_fn is not None:
                     ev["prior_grads"] = [g.detach().clone() for g in prior_grad_fn()]
             if op in ("delta_energy", "maybe_reject"):
@@ -181,6 +186,7 @@ def replaying_class(base, tape: Tape, report: Report, fused_prior: bool = False)
     class Replaying(base):
         _tape_depth = 0
         _last_de = None
+        _last_pg_abs = None
 
         def _tape_call(self, op, args, kwargs):
             if self._tape_depth > 0:
@@ -195,6 +201,8 @@ def replaying_class(base, tape: Tape, report: Report, fused_prior: bool = False)
                 assert abs(have - want) <= 1e-12 * max(1.0, abs(want)), f"{op}: group[{k}] {have} != {want}"
             report.n_events += 1
             report.ops[op] = report.ops.get(op, 0) + 1
+            if "pg_abs" in ev:
+                self._last_pg_abs = ev["pg_abs"]
             if op in STEP_OPS:
                 for i, (p, g) in enumerate(zip(params, ev["grads"])):
                     if g is None:
@@ -276,7 +284,11 @@ def replaying_class(base, tape: Tape, report: Report, fused_prior: bool = False)
                         if a is None:
                             raise AssertionError(f"{op}: state[{key}] missing for tensor {i}")
                         a = float(a)
-                    if key in ("delta_energy", "prev_new_momentum_delta"):
+                    if key == "est_config_temp" and self._last_pg_abs is not None:
+                        # dot(p, g) N / d: a sum of signed terms, judged against sum |p_i g_i| N / d
+                        nd = float(self.param_groups[0]["num_data"])
+                        scale = max(abs(b), self._last_pg_abs[i] * nd / p.numel(), 1e-30)
+                    elif key in ("delta_energy", "prev_new_momentum_delta"):
                         # running sums of signed terms: judged against the size of the terms
                         mags = [abs(x) for x in wants if x is not None and math.isfinite(x)]
                         scale = max(max(mags, default=0.0), 1e-3)

@@ -60,8 +60,7 @@ def test_train_bnn_main_with_the_overlay(tmp_path, monkeypatch, inference, model
     eu = refenv.exp_utils()
     samples = eu.load_samples(os.path.join(rundir, "samples.pt"))
     assert samples["steps"].shape == (4,)
-    names = [n for n, _ in run_named_parameters(samples)]
-    assert len(names) == fg.nseg
+    assert sum(int(v[0].numel()) for k, v in samples.items() if v.dtype == torch.float32) >= fg.n_params
     for k, v in samples.items():
         if v.dtype.is_floating_point:
             assert torch.isfinite(v).all(), k
@@ -71,7 +70,3 @@ def test_train_bnn_main_with_the_overlay(tmp_path, monkeypatch, inference, model
         if inference.endswith("Reject") and extra.get("reject_samples", True):
             rejected = f["acceptance/rejected"][:]
             assert (rejected != -2 ** 63).sum() == 5
-
-
-def run_named_parameters(samples):
-    return [(k, v) for k, v in samples.items() if k.endswith(".p")]
