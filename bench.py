@@ -13,13 +13,17 @@ from the reference's get_model), synthetic gradients.  The working set
 One JSON line on stdout (rank 0):
   value        param-updates/s, all ranks, inputs resident in HBM, through the
                sampler's public API (`opt.step`)
-  roofline     12 B/param algorithmic bytes / kernel time (CUDA events around
-               back-to-back C-ABI launches) against MEASURED_PEAKS.json
+  roofline     12 B/param algorithmic bytes / kernel time against MEASURED_PEAKS.json, in BOTH
+               regimes: `frac` = back-to-back C-ABI launches (launch k+1 starts on what launch k
+               left in L2), `production` = the same launch with the L2 evicted in between, which
+               is what a training loop sees (a forward/backward pass sits between two steps)
+  samplers     the same two numbers for VerletSGLD.step and HMC.step, all ranks
   e2e          same metric with the step's gradient coming from pinned HOST memory
                and the diagnostics read back to the host every step
   cpu_baseline the numpy oracle port of the reference sampler on the host cores
-`--impl reference` times the reference algorithm's CPU port (oracle/, all host
-threads) on the same workload.
+`--impl reference` times the reference's CPU sampler on the same workload: the
+unmodified `bnn_priors.mcmc` classes from oracle/_ref (when the snapshot is there)
+next to the two ports under oracle/; `value` is the fastest of them.
 """
 from __future__ import annotations
 
@@ -40,6 +44,20 @@ UNIT = "param-updates/s"
 WORKLOAD = "vwidth_resnet18_w96_cifar10_gaussian"
 HP = dict(lr=5e-4, num_data=50000.0, momentum=0.994, temperature=1.0)
 ALG_BYTES_PER_PARAM = 12          # p, grad, momentum as fp32 (BASELINE.json north_star)
+
+
+def workload_config(world: int, n_params: int, tensors: int, total_floats: int) -> dict:
+    "what is being computed -- identical keys and values in both arms (`--impl reference` and the GPU arm)"
+    return {"workload": WORKLOAD, "n_params": n_params, "tensors": tensors, "sampler": "SGLD",
+            "calc_metrics": False, **HP, "chains": world,
+            "parallelism": f"{world} independent chains, no per-step collective",
+            "l2": "inputs (3 x %.0f MB) larger than the 126 MB L2, no flush inside the timed loop" % (4 * total_floats / 1e6)}
+
+
+def padded_total(tensors) -> int:
+    "floats of one flat array in the chain's layout (segments start on 32-float lines)"
+    import numpy as np
+    return int(sum((int(np.prod(t["shape"]) if t["shape"] else 1) + 31) // 32 * 32 for t in tensors))
 
 
 def load_tensors(tag=WORKLOAD):
@@ -200,34 +218,112 @@ def time_cpu_torch(steps: int, warmup: int, threads: int):
     return dt / steps, sum(int(p.numel()) for p in params)
 
 
+def reference_package():
+    """The unmodified reference (`bnn_priors.mcmc`) from the oracle/_ref snapshot, or None.  The snapshot
+    is made by oracle/make_ref.py in the build container and travels with the tree; nothing outside
+    `--impl reference` and tests/ imports it."""
+    root = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(root, "bnn_priors", "mcmc", "sgld.py")):
+        return None
+    sys.dont_write_bytecode = True
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import importlib
+    return importlib.import_module("bnn_priors.mcmc")          # needs torch + numpy only (mcmc/sgld.py:1-6)
+
+
+def time_reference_package(ref, threads: int, steps: int, warmup: int):
+    """the reference's own classes, CPU tensors of the workload's shapes, all host
+    threads for ATen.  Returns {call: {ms_per_step, value, steps}}."""
+    import torch
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    tensors = load_tensors()
+
+    def fresh():
+        ps = [torch.nn.Parameter(torch.randn(tuple(t["shape"]), generator=g) * (t["scale"] if t["kind"] else 1.0))
+              for t in tensors]
+        for p in ps:
+            p.grad = torch.randn(p.shape, generator=g) * 1e-3
+        return ps
+    n = sum(int(p.numel()) for p in fresh())
+    out = {}
+
+    def timed(name, fn, k, w):
+        for _ in range(w):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            fn()
+        sec = (time.perf_counter() - t0) / k
+        out[name] = {"ms_per_step": sec * 1e3, "value": n / sec, "steps": k, "warmup": w, "kind": "reference"}
+
+    ps = fresh()
+    opt = ref.SGLD(ps, **HP)
+    opt.sample_momentum()
+    timed("SGLD.step(calc_metrics=False)", lambda: opt.step(calc_metrics=False), steps, warmup)
+    few = max(2, min(steps, 5))
+    timed("SGLD.step(calc_metrics=True)", lambda: opt.step(calc_metrics=True), few, 1)
+    del opt
+    opt = ref.VerletSGLD(ps, **HP)
+    opt.sample_momentum()
+    timed("VerletSGLD.initial_step(save_state=True)", lambda: opt.initial_step(save_state=True, calc_metrics=False), few, 1)
+    timed("VerletSGLD.step(calc_metrics=False)", lambda: opt.step(calc_metrics=False), few, 1)
+    timed("VerletSGLD.step(calc_metrics=True)", lambda: opt.step(calc_metrics=True), few, 1)
+    timed("VerletSGLD.final_step(calc_metrics=True)", lambda: opt.final_step(calc_metrics=True), few, 1)
+    timed("VerletSGLD.delta_energy", lambda: opt.delta_energy(1.0, 1.1), few, 1)
+    for gr in opt.param_groups:
+        gr["temperature"] = 1e-30                 # the Metropolis test always rejects: the restore is timed
+    timed("VerletSGLD.maybe_reject(rejecting)", lambda: opt.maybe_reject(1e30), few, 1)
+    del opt
+    opt = ref.HMC(ps, lr=HP["lr"], num_data=HP["num_data"], raise_on_nan=False)
+    opt.sample_momentum()
+    opt.initial_step(save_state=False, calc_metrics=False)
+    timed("HMC.step(calc_metrics=False)", lambda: opt.step(calc_metrics=False), few, 1)
+    timed("HMC.step(calc_metrics=True)", lambda: opt.step(calc_metrics=True), few, 1)
+    return out, n
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 40))
-    warmup = max(1, min(args.warmup, 3))
-    # (a) the numpy port, the 25M chain cut into one sub-chain per host thread (parallel noise)
-    sec_np, n_params, used = time_cpu(steps, warmup, threads)
-    # (b) the reference's own torch op sequence, all host threads for ATen's intra-op parallelism;
-    #     bounded: its serial randn_like makes a step take ~0.3 s
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # (a) the numpy port, the 25M chain cut into one sub-chain per host thread (parallel noise):
+    #     exactly --steps / --warmup
+    sec_np, n_params, used = time_cpu(steps, max(1, warmup), threads)
+    arms = {"numpy_port_one_subchain_per_thread": {"ms_per_step": sec_np * 1e3, "value": n_params / sec_np, "steps": steps,
+                                                   "warmup": max(1, warmup), "kind": "port", "cores": used}}
+    # (b) the reference's own torch op sequence restated (oracle/sgmcmc_torch.py), all host threads for
+    #     ATen's intra-op parallelism; bounded: its serial randn_like makes a step take ~0.3 s
     t_steps = max(2, min(steps, 12))
     sec_t, _ = time_cpu_torch(t_steps, 1, threads)
-    arms = {"numpy_port_one_subchain_per_thread": {"ms_per_step": sec_np * 1e3, "value": n_params / sec_np, "steps": steps},
-            "torch_ops_like_the_reference": {"ms_per_step": sec_t * 1e3, "value": n_params / sec_t, "steps": t_steps}}
-    # headline of this arm: the FASTER of the two (the stronger CPU baseline)
+    arms["torch_ops_like_the_reference"] = {"ms_per_step": sec_t * 1e3, "value": n_params / sec_t, "steps": t_steps,
+                                            "warmup": 1, "kind": "port", "cores": threads}
+    # (c) the UNMODIFIED reference classes (oracle/_ref), BASELINE.md section 4; bounded like (b)
+    ref = reference_package()
+    ref_calls = None
+    if ref is not None:
+        ref_calls, _ = time_reference_package(ref, threads, t_steps, 1)
+        main = ref_calls["SGLD.step(calc_metrics=False)"]
+        arms["reference_bnn_priors_mcmc_SGLD"] = dict(main, cores=threads)
+    # headline of this arm: the FASTEST CPU arm (the strongest baseline, so the ratio is conservative)
     best = min(arms, key=lambda k: arms[k]["ms_per_step"])
     sec = arms[best]["ms_per_step"] * 1e-3
     value = n_params / sec
+    tensors = load_tensors()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": arms[best]["steps"], "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": arms[best]["steps"], "warmup": arms[best]["warmup"], "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_params": n_params, "sampler": "SGLD", **HP,
-                   "note": "CPU arms of the reference algorithm on the host cores; value = the faster one (" + best + ")"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
+        "config": workload_config(args.gpus, n_params, len(tensors), padded_total(tensors)),
+        "impl_notes": "CPU arms of the reference sampler on the host cores (one chain, however many GPUs the other "
+                      "arm uses); value = the fastest arm (" + best + ")",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arms[best]["cores"], "kind": arms[best]["kind"],
                          "sample": f"{arms[best]['steps']} full SGLD steps over all {n_params} parameters ({best})"},
         "cpu_arms": arms,
+        "reference_calls": ref_calls,      # BASELINE.md section 4 table, from the unmodified reference (None: no snapshot)
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -279,12 +375,72 @@ def timed_gpu(fn, steps, device, dist_on):
     e1.record()
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1)
+    return max_over_ranks(ms, device, dist_on)
+
+
+def max_over_ranks(ms, device, dist_on):
+    if not dist_on:
+        return ms
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    return float(t.item())
+
+
+class L2Flush:
+    """Evicts the 126 MB L2 between two timed launches: a 512 MB buffer overwritten by a memset
+    (what a forward / backward pass does to the L2 between two sampler steps of a training loop)."""
+
+    def __init__(self, device, mbytes=512):
+        import torch
+        self.buf = torch.empty(mbytes * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def timed_flushed(fn, steps, device, dist_on, flush, before=None):
+    """Mean milliseconds of ONE call of fn with the L2 evicted before each call: a CUDA event pair
+    around every call (the flush and `before` -- host-side preparation such as zero_grad() -- are
+    outside the pairs), max over ranks."""
+    import torch
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     if dist_on:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        import torch.distributed as dist
         dist.barrier()
-    return ms
+    torch.cuda.synchronize(device)
+    for e0, e1 in pairs:
+        if before is not None:
+            before()
+        flush()
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize(device)
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in pairs) / steps
+    return max_over_ranks(ms, device, dist_on)
+
+
+def regime_numbers(fg, n, K, device, dist_on, flush, peak):
+    """kernel time of the chain's LAST launch re-issued through the C ABI, in three regimes"""
+    for _ in range(3):
+        fg.relaunch()
+    back_to_back = timed_gpu(fg.relaunch, K, device, dist_on) / K
+    fg.serpentine = False            # every launch in the same direction: nothing useful left in L2
+    for _ in range(3):
+        fg.relaunch()
+    same_dir = timed_gpu(fg.relaunch, K, device, dist_on) / K
+    fg.serpentine = True
+    Kp = max(5, min(K, 50))
+    production = timed_flushed(fg.relaunch, Kp, device, dist_on, flush)
+    alg = ALG_BYTES_PER_PARAM * n
+
+    def f(ms):
+        return {"kernel_us": ms * 1e3, "achieved": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                "touched_GBs": 20 * n / (ms * 1e-3) / 1e9, "touched_frac": 20 * n / (ms * 1e-3) / 1e9 / peak}
+    return f(back_to_back), f(same_dir), f(production)
 
 
 def run_gpu(args):
@@ -299,9 +455,11 @@ def run_gpu(args):
     if dist_on:
         import torch.distributed as dist
     K, W = args.steps, max(3, args.warmup)
+    peak, peak_src = measured_peak()
+    flush = L2Flush(device)
 
     opt, params, fg = make_chain(device, CH.chain_seed(0, rank))
-    n = fg.n_params
+    n, nseg, total = fg.n_params, fg.nseg, fg.total
     step = lambda: opt.step(calc_metrics=False)   # noqa: E731
     sampler = ClockSampler(device.index)
 
@@ -312,18 +470,37 @@ def run_gpu(args):
     l0 = fg.launches
     ms_api = timed_gpu(step, K, device, dist_on)
     launches = fg.launches - l0
+    # host cost of one opt.step (enqueue only), for the record
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step()
+    host_us = (time.perf_counter() - t0) / K * 1e6
+    torch.cuda.synchronize(device)
 
-    # kernel time: back-to-back launches of the same argument block through the C ABI
+    # ---- kernel time: back-to-back launches / same direction / L2 evicted in between (production)
+    r_b2b, r_same, r_prod = regime_numbers(fg, n, K, device, dist_on, flush, peak)
+
+    # ---- the reference runner's loop: zero_grad() drops p.grad, backward() hands every gradient over
+    #      in a tensor of its own, the L2 is gone; the step reads those tensors in place (no copy)
+    grad_bufs = [torch.randn_like(p) * 1e-3 for p in params]
+
+    def foreign_grads():
+        opt.zero_grad()
+        for p, gb in zip(params, grad_bufs):
+            p.grad = gb.view_as(gb)          # a new tensor object at the address the allocator re-uses
+    Kp = max(5, min(K, 50))
     for _ in range(3):
-        fg.relaunch()
-    ms_kernel = timed_gpu(fg.relaunch, K, device, dist_on) / K
-    # the same launches all walking the chain in the same direction (no reuse of what the previous
-    # launch left in L2): every byte comes from / goes to HBM
-    fg.serpentine = False
-    for _ in range(3):
-        fg.relaunch()
-    ms_kernel_cold = timed_gpu(fg.relaunch, K, device, dist_on) / K
-    fg.serpentine = True
+        foreign_grads()
+        step()
+    c0, tw0 = fg.copies, fg.table_writes
+    ms_foreign = timed_flushed(step, Kp, device, dist_on, flush, before=foreign_grads)
+    foreign = {"us_per_step": ms_foreign * 1e3, "frac": ALG_BYTES_PER_PARAM * n / (ms_foreign * 1e-3) / 1e9 / peak,
+               "gradient_copies": fg.copies - c0, "pointer_table_writes": fg.table_writes - tw0,
+               "what": "opt.step(calc_metrics=False) right after zero_grad() + gradients in tensors of their own, "
+                       "L2 evicted by a 512 MB memset before every step; CUDA events around the step only"}
+    for p, v in zip(params, fg.g_views):
+        p.grad = v
+    del grad_bufs
 
     # ---- end to end: gradient from pinned host memory in, diagnostics out, every step
     E = max(3, min(K, 30))
@@ -348,13 +525,21 @@ def run_gpu(args):
         e2e_step()
     torch.cuda.synchronize(device)
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    # the bare copy alone, same buffers: what the host side of this box can deliver to N GPUs at once
     if dist_on:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(E):
+        fg.G.copy_(host_g, non_blocking=True)
+    torch.cuda.synchronize(device)
+    h2d_ms = (time.perf_counter() - t0) * 1e3 / E
+    e2e_ms = max_over_ranks(e2e_ms, device, dist_on)
+    h2d_ms = max_over_ranks(h2d_ms, device, dist_on)
     sampler.stop()
     h2d = 4 * fg.total
     d2h = fg.nseg * N.STATE_STRIDE * 8
+    del host_g
 
     # ---- cycle-end all-gather of the samples (one per cycle, outside the step loop)
     gather_ms = None
@@ -364,26 +549,41 @@ def run_gpu(args):
         ring.gather()
         torch.cuda.synchronize(device)
         gather_ms = timed_gpu(lambda: ring.gather(), 3, device, True) / 3
+        del ring
 
-    # ---- other transitions of the path (kernel time, same chain size), for context
-    extra = {}
+    # ---- the other samplers of the path, ALL ranks (max over ranks), same chain size
+    samplers = {}
+    Ks = max(5, min(K, 100))
+    for name, smp in (("VerletSGLD.step", "VerletSGLD"), ("HMC.step", "HMC")):
+        del opt, params, fg
+        torch.cuda.empty_cache()
+        opt, params, fg = make_chain(device, CH.chain_seed(0, rank), smp)
+        sstep = lambda: opt.step(calc_metrics=False)   # noqa: E731
+        for _ in range(W):
+            sstep()
+        ms = timed_gpu(sstep, Ks, device, dist_on)
+        b2b, _, prod = regime_numbers(fg, n, Ks, device, dist_on, flush, peak)
+        samplers[name] = {"value": world * n * Ks / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / Ks, "steps": Ks,
+                          "kernel_us": b2b["kernel_us"], "frac": b2b["frac"],
+                          "production_kernel_us": prod["kernel_us"], "production_frac": prod["frac"]}
+
+    # ---- other transitions of the path (kernel time, rank 0), for context
+    extra = {"SGLD.step after zero_grad()+foreign grads, L2 flushed": foreign}
     if rank == 0 and not args.no_extra:
-        del host_g
         for name, smp, fused, call in (
-                ("VerletSGLD.step", "VerletSGLD", False, lambda o: o.step(calc_metrics=False)),
                 ("VerletSGLD.step+fused_prior", "VerletSGLD", True, lambda o: o.step(calc_metrics=False)),
+                ("VerletSGLD.step(calc_metrics=True)", "VerletSGLD", False, lambda o: o.step(calc_metrics=True)),
                 ("VerletSGLD.initial_step(save_state)", "VerletSGLD", False,
                  lambda o: o.initial_step(save_state=True, calc_metrics=False)),
-                ("HMC.step", "HMC", False, lambda o: o.step(calc_metrics=False))):
+                ("HMC.initial_step(save_state)", "HMC", False,
+                 lambda o: o.initial_step(save_state=True, calc_metrics=False))):
             del opt, params, fg
             torch.cuda.empty_cache()
             opt, params, fg = make_chain(device, 0, smp, fused_prior=fused)
             call(opt)
-            for _ in range(3):
-                fg.relaunch()
-            ms = timed_gpu(fg.relaunch, min(K, 50), device, False) / min(K, 50)
-            extra[name] = {"us_per_step": ms * 1e3, "param_updates_per_s": n / (ms * 1e-3),
-                           "alg_GBs": ALG_BYTES_PER_PARAM * n / (ms * 1e-3) / 1e9}
+            b2b, _, prod = regime_numbers(fg, n, min(K, 50), device, False, flush, peak)
+            extra[name] = {"us_per_step": b2b["kernel_us"], "production_us_per_step": prod["kernel_us"],
+                           "param_updates_per_s": n / (b2b["kernel_us"] * 1e-6), "alg_GBs": b2b["achieved"]}
 
         # hierarchical priors: every prior-carrying weight tensor gets a sampled scale
         # (NormalGamma); a step = the step launch + its epilogue launch (BNNP_F_HYPER_POST), timed
@@ -428,36 +628,40 @@ def run_gpu(args):
 
     if rank != 0:
         return
-    peak, peak_src = measured_peak()
     traffic, traffic_cold = ncu_traffic()
-    achieved = ALG_BYTES_PER_PARAM * n / (ms_kernel * 1e-3) / 1e9
     value = world * n * K / (ms_api * 1e-3)
+    ms_kernel = r_b2b["kernel_us"] * 1e-3
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_api / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_params": n, "tensors": fg.nseg, "sampler": "SGLD",
-                   "calc_metrics": False, "noise": "in-kernel Philox4x32-10 + Box-Muller", **HP,
-                   "chains": world, "parallelism": f"{world} independent chains, no per-step collective",
-                   "l2": "inputs (3 x %.0f MB) larger than the 126 MB L2, no flush; consecutive launches walk the "
-                         "chain in opposite directions, so each starts on the lines the previous one left in L2"
-                         % (4 * fg.total / 1e6)},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "kernel_us": ms_kernel * 1e3,
+        "config": workload_config(world, n, nseg, total),
+        "impl_notes": {"noise": "in-kernel Philox4x32-10 + Box-Muller",
+                       "l2": "consecutive launches walk the chain in opposite directions, so each starts on the lines "
+                             "the previous one left in L2 (roofline.frac); roofline.production evicts the L2 in between",
+                       "host_us_per_step": host_us},
+        "roofline": {"bound": "hbm", "achieved": r_b2b["achieved"], "peak": peak, "unit": "GB/s",
+                     "frac": r_b2b["frac"], "traffic": traffic,
+                     "traffic_source": "ncu capture committed as profiles/ncu_step_kernel.json (not measured in this run)",
+                     "peak_source": peak_src, "kernel_us": r_b2b["kernel_us"],
                      "alg_bytes_per_launch": ALG_BYTES_PER_PARAM * n,
-                     # every launch in the same direction: all 20 B/param (read p, g, m; write p, m) cross the HBM pins
-                     "same_direction": {"kernel_us": ms_kernel_cold * 1e3, "traffic": traffic_cold,
-                                        "frac": ALG_BYTES_PER_PARAM * n / (ms_kernel_cold * 1e-3) / 1e9 / peak,
-                                        "touched_bytes_per_launch": 20 * n,
-                                        "touched_GBs": 20 * n / (ms_kernel_cold * 1e-3) / 1e9,
-                                        "touched_frac": 20 * n / (ms_kernel_cold * 1e-3) / 1e9 / peak},
+                     # what a training loop sees: the L2 evicted between two steps (512 MB memset), one CUDA
+                     # event pair per launch; all 20 B/param (read p, g, m; write p, m) cross the HBM pins
+                     "production": dict(r_prod, traffic=traffic_cold, touched_bytes_per_launch=20 * n,
+                                        how="L2 evicted by a 512 MB memset before every launch; event pair per launch"),
+                     # every launch in the same direction, back to back (no useful L2 carry-over either)
+                     "same_direction": dict(r_same, traffic=traffic_cold, touched_bytes_per_launch=20 * n),
                      # alternating directions (the default): part of the 20 B/param is served by L2
                      "dram_GBs": (traffic / (ms_kernel * 1e-3) / 1e9) if traffic else None,
                      "dram_frac": (traffic / (ms_kernel * 1e-3) / 1e9 / peak) if traffic else None},
+        "samplers": samplers,
         "cpu_baseline": cpu,
         "e2e": {"value": world * n * E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": E, "ms_per_step": e2e_ms / E},
+                "d2h_bytes_per_step": d2h, "steps": E, "ms_per_step": e2e_ms / E,
+                "bare_h2d_ms": h2d_ms, "bare_h2d_GBs_per_gpu": h2d / (h2d_ms * 1e-3) / 1e9,
+                "note": "per step: the gradient (4 B/param) from pinned host memory in, the per-tensor diagnostics "
+                        "(not the parameters: the chain stays resident) out; bare_h2d_* = the same copy alone, all "
+                        "ranks at once -- the host-side ceiling of this box"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "extra": extra,

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import struct
 
 import numpy as np
 
@@ -15,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BNNP_LIB") or os.path.join(HERE, "_lib", "libbnnp.so")
 
 # ---- constants of include/bnnp.h (tests/test_abi.py checks them against the header)
-ABI_VERSION = 8
+ABI_VERSION = 9
 SEG_ALIGN = 32
 THREADS = 256
 UNROLL = 4
@@ -74,22 +75,54 @@ class BnnpEpilogue(C.Structure):
     ]
 
 
+class BnnpCoef(C.Structure):
+    _fields_ = [("cm", C.c_double), ("cg", C.c_double), ("cn", C.c_double), ("cp", C.c_double),
+                ("inv_num_data", C.c_double), ("c_gm_base", C.c_double), ("curv_base", C.c_double),
+                ("rms_alpha", C.c_double)]
+
+
+COEF_SLOTS = 4
+SLOT_OTHER = 3          # sample_momentum / reduce / pre-pass launches (slots 0..2: the sampler's phases)
+
+
+class BnnpControl(C.Structure):
+    _fields_ = [("call", C.c_uint64), ("parity", C.c_int32), ("reserved", C.c_int32),
+                ("pending", BnnpEpilogue), ("coef", BnnpCoef * COEF_SLOTS)]
+
+
 class BnnpLaunch(C.Structure):
     _fields_ = [
         ("P", C.c_void_p), ("G", C.c_void_p), ("M", C.c_void_p),
         ("prev_p", C.c_void_p), ("prev_g", C.c_void_p), ("prev_m", C.c_void_p),
         ("replay_noise", C.c_void_p),
-        ("segs", C.c_void_p), ("chunks", C.c_void_p), ("chunk_ids", C.c_void_p), ("seg_state", C.c_void_p),
+        ("segs", C.c_void_p), ("chunks", C.c_void_p), ("chunk_ids", C.c_void_p),
+        ("seg_grad", C.c_void_p), ("ctl", C.c_void_p), ("seg_state", C.c_void_p),
         ("partials", C.c_void_p), ("stamps", C.c_void_p),
         ("nseg", C.c_int32), ("nchunks", C.c_int32), ("nchunks_total", C.c_int32), ("parity", C.c_int32),
         ("op", C.c_int32), ("phase", C.c_int32), ("noise", C.c_int32),
-        ("flags", C.c_uint32), ("key0", C.c_uint32), ("key1", C.c_uint32),
+        ("flags", C.c_uint32), ("coef_slot", C.c_int32), ("reserved", C.c_int32),
+        ("key0", C.c_uint32), ("key1", C.c_uint32),
         ("call", C.c_uint64),
         ("cm", C.c_double), ("cg", C.c_double), ("cn", C.c_double), ("cp", C.c_double),
         ("inv_num_data", C.c_double), ("grad_max", C.c_double),
         ("c_gm_base", C.c_double), ("curv_base", C.c_double), ("rms_alpha", C.c_double),
         ("pending", BnnpEpilogue),
     ]
+
+
+# The part of BnnpLaunch that changes from launch to launch is contiguous (nchunks .. pending): the
+# host writes it with ONE struct.pack_into instead of ~35 ctypes field stores.
+#   nchunks nchunks_total parity | op phase noise flags | coef_slot reserved | key0 key1 | call |
+#   cm cg cn cp inv_num_data grad_max c_gm_base curv_base rms_alpha |
+#   pending: valid op phase flags parity reserved call c_gm_base curv_base rms_alpha inv_num_data
+DYN_OFFSET = BnnpLaunch.nchunks.offset
+DYN_STRUCT = struct.Struct("<3i3iI2i2IQ9d" + "3iI2iQ4d")
+assert DYN_OFFSET + DYN_STRUCT.size == C.sizeof(BnnpLaunch), "BnnpLaunch layout changed: fix DYN_STRUCT"
+assert BnnpLaunch.pending.offset == DYN_OFFSET + struct.calcsize("<3i3iI2i2IQ9d")
+PENDING_STRUCT = struct.Struct("<3iI2iQ4d")
+assert PENDING_STRUCT.size == C.sizeof(BnnpEpilogue)
+COEF_STRUCT = struct.Struct("<8d")
+assert COEF_STRUCT.size == C.sizeof(BnnpCoef)
 
 
 # ---- include/bnnp_eval.h
@@ -109,7 +142,8 @@ class BnnpEvalState(C.Structure):
 EVAL_EXPORTS = ("bnnp_eval_batch", "bnnp_eval_finish", "bnnp_eval_last_error")
 
 EXPORTS = ("bnnp_abi_version", "bnnp_last_error", "bnnp_device_info", "bnnp_max_ctas_per_sm",
-           "bnnp_plan_layout", "bnnp_launch", "bnnp_finalize", "bnnp_rollback", "bnnp_probe_stream")
+           "bnnp_plan_layout", "bnnp_launch", "bnnp_finalize", "bnnp_advance", "bnnp_clear_pending", "bnnp_poke",
+           "bnnp_rollback", "bnnp_probe_stream")
 
 
 class BnnpError(RuntimeError):
@@ -137,6 +171,9 @@ def lib() -> C.CDLL:
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p]
     l.bnnp_launch.argtypes = [C.POINTER(BnnpLaunch), C.c_void_p]
     l.bnnp_finalize.argtypes = [C.POINTER(BnnpLaunch), C.c_void_p]
+    l.bnnp_advance.argtypes = [C.POINTER(BnnpLaunch), C.c_void_p]
+    l.bnnp_clear_pending.argtypes = [C.c_void_p, C.c_void_p]
+    l.bnnp_poke.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     l.bnnp_rollback.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
     l.bnnp_probe_stream.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
     l.bnnp_eval_batch.argtypes = [C.POINTER(BnnpEvalState), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

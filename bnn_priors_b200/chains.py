@@ -20,10 +20,43 @@ import torch
 import torch.distributed as dist
 
 
+def pin_host_cores(local_rank: int, local_world: int) -> Optional[List[int]]:
+    """Give this rank its own slice of the host cores its GPU is closest to (NVML's CPU affinity of
+    the device = the NUMA node the GPU hangs off), so that the launch threads of N chains neither
+    migrate nor share a core, and first-touch places this rank's pinned staging buffers on that
+    node.  Returns the cores chosen, or None if nothing was changed (no NVML, one rank, or
+    BNNP_PIN_CORES=0)."""
+    if local_world <= 1 or os.environ.get("BNNP_PIN_CORES", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    allowed = sorted(os.sched_getaffinity(0))
+    near = allowed
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed) // 64) + 1)
+        gpu_cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        if gpu_cpus & set(allowed):
+            near = sorted(gpu_cpus & set(allowed))
+    except Exception:
+        pass
+    per = len(near) // local_world
+    if per < 1:
+        return None
+    # ranks that share an affinity set split it evenly (on this pod: one NUMA node, 32 cores, 8 GPUs)
+    mine = near[local_rank * per:(local_rank + 1) * per]
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return None
+    return mine
+
+
 def init_chains(backend: Optional[str] = None) -> tuple:
     """Join the process group described by RANK / WORLD_SIZE / LOCAL_RANK /
-    MASTER_ADDR / MASTER_PORT (torchrun) and pin this process to its GPU.
-    Returns (rank, world_size, device).  A single process needs no group."""
+    MASTER_ADDR / MASTER_PORT (torchrun), pin this process to its GPU and to its own slice of
+    the host cores next to that GPU.  Returns (rank, world_size, device).  A single process needs
+    no group."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -31,6 +64,7 @@ def init_chains(backend: Optional[str] = None) -> tuple:
     device = torch.device("cuda", local) if use_cuda else torch.device("cpu")
     if use_cuda:
         torch.cuda.set_device(device)
+        pin_host_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         kw = {}

@@ -311,14 +311,26 @@ union F4 {
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st_f4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 
-// L2 eviction-priority hints (createpolicy encodings; PTX ld/st .L2::cache_hint).  Consecutive
+// L2 eviction-priority hints (PTX createpolicy + ld/st .L2::cache_hint).  Consecutive
 // launches walk the chain in opposite directions (BNNP_F_REVERSE), so what a launch leaves in the
 // 126 MB L2 is what the next one reads first.  A parameter / momentum line kept there saves a DRAM
 // read AND a write-back, so P and M are accessed evict-last; the snapshot stores (read again only
 // after a rejection) are evict-first.  Measured (profiles/r01f_notes.md): serpentine order 79.1 ->
 // 69.7 us per SGLD step, + evict-last P/M 67.5 us; evict-first gradient loads made no difference.
-constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
-constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
+// The policy words come from createpolicy (ptxas folds the instruction with a constant fraction
+// into an immediate, so this costs nothing over a hard-coded encoding and does not depend on one).
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#define POLICY_EVICT_FIRST policy_evict_first()
+#define POLICY_EVICT_LAST policy_evict_last()
 #ifndef BNNP_G_POLICY
 #define BNNP_G_POLICY 0     // 0: plain loads, 1: evict-first
 #endif
@@ -365,6 +377,44 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 struct Coef {
     float cm, cgM, cn, cpM, gmax;
 };
+
+// What changes from launch to launch.  Normally kernel parameters (constant bank); in capturable
+// mode (BnnpLaunch.ctl) read from the chain's device control block, so that a captured launch can
+// be replayed with a new Philox counter, the other walking direction and other coefficients.
+struct Dyn {
+    uint64_t call;
+    int parity;
+    uint32_t flags;
+    float cm, cn;
+    double cg, cp, inv_n;
+};
+
+__device__ __forceinline__ Dyn load_dyn(const StepParams& S) {
+    const BnnpLaunch& L = S.L;
+    Dyn d;
+    if (L.ctl == nullptr) {
+        d.call = L.call;
+        d.parity = L.parity;
+        d.flags = L.flags;
+        d.cm = S.cm;
+        d.cn = S.cn;
+        d.cg = L.cg;
+        d.cp = L.cp;
+        d.inv_n = L.inv_num_data;
+    } else {
+        const BnnpControl* ctl = L.ctl;
+        const BnnpCoef* cf = &ctl->coef[L.coef_slot];
+        d.call = ctl->call;
+        d.parity = ctl->parity;
+        d.flags = d.parity ? (L.flags | BNNP_F_REVERSE) : (L.flags & ~(uint32_t)BNNP_F_REVERSE);
+        d.cm = (float)cf->cm;
+        d.cn = (float)cf->cn;
+        d.cg = cf->cg;
+        d.cp = cf->cp;
+        d.inv_n = cf->inv_num_data;
+    }
+    return d;
+}
 
 // which dot products a launch needs (compile time: every one costs an FMA per element
 // and ten shuffle steps per warp)
@@ -562,11 +612,17 @@ __device__ __forceinline__ double fold_records(const double* base, int num_chunk
     return warp_sum_f64(t);
 }
 
-// CTA-wide: fold the partial records launch `L.pending` left for segment `seg` (one warp
+// the pending epilogue of a launch: from the kernel parameters, or from the control block
+__device__ __forceinline__ BnnpEpilogue load_pending(const BnnpLaunch& L) {
+    if (L.ctl == nullptr) return L.pending;
+    return L.ctl->pending;
+}
+
+// CTA-wide: fold the partial records launch `E` left for segment `seg` (one warp
 // per sum, lanes over the chunks, fp64, fixed order) and apply its epilogue.  A segment
 // the pending launch skipped carries an older stamp and is left alone.
-__device__ void apply_pending(const BnnpLaunch& L, const BnnpSegment& sd, int seg, double* s_sum) {
-    const BnnpEpilogue& E = L.pending;
+__device__ void apply_pending(const BnnpLaunch& L, const BnnpEpilogue& E, const BnnpSegment& sd, int seg,
+                              double* s_sum) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rec0 = (int64_t)E.parity * L.nchunks_total + sd.first_chunk;
     if (L.stamps[rec0] != E.call + 1) return;     // uniform over the CTA
@@ -619,8 +675,7 @@ template <int NOISE, bool PRIOR, int KIND, bool NOISE_FIRST, int SUMS>
 __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCtx& cx, const Coef& c,
                                               const PriorConst& pc, const PhiloxKeys& keys, F4 (&p)[UNROLL],
                                               F4 (&g)[UNROLL], F4 (&m)[UNROLL], F4 (&z)[UNROLL],
-                                              float acc[BNNP_NRED]) {
-    const uint32_t flags = L.flags;
+                                              float acc[BNNP_NRED], const uint32_t flags, const uint64_t call) {
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const int e = (u * THREADS + cx.tid) * 4;
@@ -631,7 +686,7 @@ __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCt
             st_f4_hint(L.prev_g + fi, g[u].v, POLICY_EVICT_FIRST);
             if (L.prev_m != nullptr) st_f4_hint(L.prev_m + fi, m[u].v, POLICY_EVICT_FIRST);
         }
-        if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)fi >> 2, L.call, keys, z[u].f);
+        if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)fi >> 2, call, keys, z[u].f);
         const int valid = cx.rem - e;
         if (valid < 4) {   // the quad that straddles the segment end: padding lanes are zeros
 #pragma unroll
@@ -666,25 +721,31 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     const PhiloxKeys& keys = S.keys;
 
     const int tid = threadIdx.x;
-    const int slot = (L.flags & BNNP_F_REVERSE) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const Dyn dyn = load_dyn(S);
+    const uint32_t flags = dyn.flags;
+    const int slot = (flags & BNNP_F_REVERSE) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
     const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[slot] : slot;
     const ChunkDesc cd = load_chunk(L.chunks, chunk);
     const int seg = cd.seg;
     const BnnpSegment sd = L.segs[seg];
+    // the segment's gradient: its slice of the flat G, or the tensor autograd handed over
+    const float* gsrc = L.seg_grad != nullptr ? L.seg_grad[seg] + (cd.fbase - sd.off) : L.G + cd.fbase;
     // the previous launch's bookkeeping: segment j is handled by CTA j, i.e. by the CTAs that
     // start first, so the few microseconds it takes are absorbed at the front of the launch
-    if (L.pending.valid && (int)blockIdx.x < L.nseg) apply_pending(L, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
+    if ((int)blockIdx.x < L.nseg) {
+        const BnnpEpilogue E = load_pending(L);
+        if (E.valid) apply_pending(L, E, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
+    }
     ChunkCtx cx;
     cx.rem = cd.rem;
     cx.fbase = cd.fbase;
     cx.tid = tid;
-    const uint32_t flags = L.flags;
 
     Coef c;
-    c.cm = S.cm;
-    c.cn = S.cn;
-    c.cgM = (float)(L.cg * sd.precond);
-    c.cpM = (float)(L.cp * sd.precond);
+    c.cm = dyn.cm;
+    c.cn = dyn.cn;
+    c.cgM = (float)(dyn.cg * sd.precond);
+    c.cpM = (float)(dyn.cp * sd.precond);
     c.gmax = S.gmax;
 
     // ---- front-batched 128-bit loads: 3 (4 with replay noise) x UNROLL in flight per thread
@@ -695,7 +756,7 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
         const int e = (u * THREADS + tid) * 4;
         const bool act = e < cx.rem;
         p[u].v = (act && (flags & BNNP_F_READ_P)) ? ld_state(L.P + cx.fbase + e) : zero4;
-        g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_grad(L.G + cx.fbase + e) : zero4;
+        g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_grad(gsrc + e) : zero4;
         m[u].v = (act && (flags & BNNP_F_READ_M)) ? ld_state(L.M + cx.fbase + e) : zero4;
         if (NOISE == BNNP_NOISE_REPLAY) z[u].v = act ? ld_f4(L.replay_noise + cx.fbase + e) : zero4;
         else z[u].v = zero4;
@@ -714,8 +775,8 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
         }
 #define BNNP_FORM_CASE(F)                                                                                      \
     case F:                                                                                                    \
-        process_chunk<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, L.inv_num_data, hyper_term), \
-                                                         keys, p, g, m, z, acc);                               \
+        process_chunk<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, dyn.inv_n, hyper_term),    \
+                                                         keys, p, g, m, z, acc, flags, dyn.call);              \
         break;
         switch (prior_form(sd.prior_kind)) {   // uniform over the CTA: one closed form per segment
             BNNP_FORM_CASE(F_NORMAL)
@@ -731,7 +792,7 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
         }
 #undef BNNP_FORM_CASE
     } else {
-        process_chunk<NOISE, false, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, PriorConst(), keys, p, g, m, z, acc);
+        process_chunk<NOISE, false, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, PriorConst(), keys, p, g, m, z, acc, flags, dyn.call);
     }
 
     // ---- chunk reduction: fp32 butterfly inside the warp, fp64 across warps (fixed order)
@@ -754,9 +815,9 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < NWARPS; ++w) s += s_red[w][tid];
-        L.partials[((int64_t)L.parity * L.nchunks_total + chunk) * BNNP_NRED + tid] = s;
+        L.partials[((int64_t)dyn.parity * L.nchunks_total + chunk) * BNNP_NRED + tid] = s;
     }
-    if (tid == 0) L.stamps[(int64_t)L.parity * L.nchunks_total + chunk] = L.call + 1;   // "this launch wrote it"
+    if (tid == 0) L.stamps[(int64_t)dyn.parity * L.nchunks_total + chunk] = dyn.call + 1;   // "this launch wrote it"
 }
 
 // ---------------------------------------------------------------------------------
@@ -791,11 +852,15 @@ __global__ void __launch_bounds__(THREADS, BNNP_PREPASS_CTAS) bnnp_prepass_kerne
     __shared__ double s_red[NWARPS][BNNP_NRED];
     const BnnpLaunch& L = S.L;
     const int tid = threadIdx.x;
-    const int chunk = (L.flags & BNNP_F_REVERSE) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const Dyn dyn = load_dyn(S);
+    const int chunk = (dyn.flags & BNNP_F_REVERSE) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
     const ChunkDesc cd = load_chunk(L.chunks, chunk);
     const int seg = cd.seg;
     BnnpSegment sd = L.segs[seg];
-    if (L.pending.valid && (int)blockIdx.x < L.nseg) apply_pending(L, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
+    if ((int)blockIdx.x < L.nseg) {
+        const BnnpEpilogue E = load_pending(L);
+        if (E.valid) apply_pending(L, E, L.segs[blockIdx.x], blockIdx.x, s_red[0]);
+    }
     ChunkCtx cx;
     cx.rem = cd.rem;
     cx.fbase = cd.fbase;
@@ -815,7 +880,7 @@ __global__ void __launch_bounds__(THREADS, BNNP_PREPASS_CTAS) bnnp_prepass_kerne
     float logp = 0.0f, stat = 0.0f;
     switch (prior_form(sd.prior_kind)) {
 #define BNNP_PRE_CASE(F) \
-    case F: prepass_quads<F>(make_prior<F>(sd, L.inv_num_data, 0.0f), cx, p, logp, stat); break;
+    case F: prepass_quads<F>(make_prior<F>(sd, dyn.inv_n, 0.0f), cx, p, logp, stat); break;
         BNNP_PRE_CASE(F_NORMAL)
         BNNP_PRE_CASE(F_LOGNORMAL)
         BNNP_PRE_CASE(F_LAPLACE)
@@ -843,16 +908,52 @@ __global__ void __launch_bounds__(THREADS, BNNP_PREPASS_CTAS) bnnp_prepass_kerne
 #pragma unroll
             for (int w = 0; w < NWARPS; ++w) s += s_red[w][k];
         }
-        L.partials[((int64_t)L.parity * L.nchunks_total + chunk) * BNNP_NRED + tid] = s;
+        L.partials[((int64_t)dyn.parity * L.nchunks_total + chunk) * BNNP_NRED + tid] = s;
     }
-    if (tid == 0) L.stamps[(int64_t)L.parity * L.nchunks_total + chunk] = L.call + 1;
+    if (tid == 0) L.stamps[(int64_t)dyn.parity * L.nchunks_total + chunk] = dyn.call + 1;
 }
 
 // bnnp_finalize: the pending epilogue of every segment, nothing else
 __global__ void __launch_bounds__(THREADS) bnnp_finalize_kernel(const BnnpLaunch L) {
     __shared__ double s_red[BNNP_NRED + 1];
     const int seg = blockIdx.x;
-    apply_pending(L, L.segs[seg], seg, s_red);
+    const BnnpEpilogue E = load_pending(L);
+    if (E.valid) apply_pending(L, E, L.segs[seg], seg, s_red);
+}
+
+// Capturable mode: the control block moves on after a launch (bnnp_advance).
+__global__ void bnnp_advance_kernel(BnnpControl* ctl, int op, int phase, uint32_t flags, int coef_slot) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const BnnpCoef cf = ctl->coef[coef_slot];
+    BnnpEpilogue E;
+    E.valid = 1;
+    E.op = op;
+    E.phase = phase;
+    E.parity = ctl->parity;
+    E.flags = E.parity ? (flags | BNNP_F_REVERSE) : (flags & ~(uint32_t)BNNP_F_REVERSE);
+    E.reserved = 0;
+    E.call = ctl->call;
+    E.c_gm_base = cf.c_gm_base;
+    E.curv_base = cf.curv_base;
+    E.rms_alpha = cf.rms_alpha;
+    E.inv_num_data = cf.inv_num_data;
+    ctl->pending = E;
+    ctl->call = E.call + 1;
+    ctl->parity = E.parity ^ 1;
+}
+
+__global__ void bnnp_clear_pending_kernel(BnnpControl* ctl) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) ctl->pending.valid = 0;
+}
+
+// bnnp_poke: the payload travels in the kernel parameters
+template <int WORDS>
+struct PokePayload {
+    uint32_t w[WORDS];
+};
+template <int WORDS>
+__global__ void bnnp_poke_kernel(uint32_t* dst, const __grid_constant__ PokePayload<WORDS> src, int nwords) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src.w[i];
 }
 
 // P,G,M <- prev_* : verlet_sgld.py:63-69
@@ -1023,17 +1124,24 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
         return fail(BNNP_E_ARG, "bnnp_launch: null table pointer");
     if (a->nchunks > a->nchunks_total || (a->chunk_ids == nullptr && a->nchunks != a->nchunks_total))
         return fail(BNNP_E_ARG, "bnnp_launch: nchunks does not match the plan");
-    if ((a->parity | 1) != 1 || (a->pending.valid && (a->pending.parity | 1) != 1))
+    // with a control block, parity / call / pending / coefficients live on the device (the caller keeps
+    // the protocol: bnnp_advance after every launch, bnnp_finalize + bnnp_clear_pending before a launch
+    // with chunk_ids or after a BNNP_F_HYPER / BNNP_F_HYPER_POST launch)
+    const bool host_state = a->ctl == nullptr;
+    if (!host_state && (a->coef_slot < 0 || a->coef_slot >= BNNP_COEF_SLOTS))
+        return fail(BNNP_E_ARG, "bnnp_launch: coef_slot out of range");
+    if (host_state && ((a->parity | 1) != 1 || (a->pending.valid && (a->pending.parity | 1) != 1)))
         return fail(BNNP_E_ARG, "bnnp_launch: parity must be 0 or 1");
-    if (a->pending.valid && a->chunk_ids != nullptr)
+    if (host_state && a->pending.valid && a->chunk_ids != nullptr)
         return fail(BNNP_E_ARG, "bnnp_launch: a launch with chunk_ids cannot carry a pending epilogue; bnnp_finalize first");
-    if (a->pending.valid && a->pending.parity == a->parity)
+    if (host_state && a->pending.valid && a->pending.parity == a->parity)
         return fail(BNNP_E_ARG, "bnnp_launch: this launch would overwrite the partial records of the pending one");
     if (a->op < BNNP_OP_SGLD || a->op > BNNP_OP_REDUCE) return fail(BNNP_E_ARG, "bnnp_launch: bad op");
     if (a->phase < BNNP_PHASE_INITIAL || a->phase > BNNP_PHASE_FINAL) return fail(BNNP_E_ARG, "bnnp_launch: bad phase");
     const uint32_t f = a->flags;
     if ((f & (BNNP_F_READ_P | BNNP_F_WRITE_P)) && a->P == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: P is null");
-    if ((f & BNNP_F_READ_G) && a->G == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: G is null");
+    if ((f & BNNP_F_READ_G) && a->G == nullptr && a->seg_grad == nullptr)
+        return fail(BNNP_E_ARG, "bnnp_launch: G and seg_grad are both null");
     if ((f & (BNNP_F_READ_M | BNNP_F_WRITE_M)) && a->M == nullptr) return fail(BNNP_E_ARG, "bnnp_launch: M is null");
     if ((f & BNNP_F_WRITE_P) && !(f & BNNP_F_READ_P)) return fail(BNNP_E_ARG, "bnnp_launch: WRITE_P needs READ_P");
     if ((f & BNNP_F_SAVE_STATE) && (a->prev_p == nullptr || a->prev_g == nullptr))
@@ -1043,7 +1151,7 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
     if (misaligned(a->P) || misaligned(a->G) || misaligned(a->M) || misaligned(a->prev_p) || misaligned(a->prev_g) ||
         misaligned(a->prev_m) || misaligned(a->replay_noise) || misaligned(a->chunks))
         return fail(BNNP_E_ALIGN, "bnnp_launch: flat arrays and the chunk table must be 16-byte aligned");
-    if (a->pending.valid && (a->pending.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)))
+    if (host_state && a->pending.valid && (a->pending.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)))
         return fail(BNNP_E_ARG, "bnnp_launch: the epilogue of a BNNP_F_HYPER / BNNP_F_HYPER_POST launch rewrites the "
                                 "segment table; bnnp_finalize first");
     if ((f & BNNP_F_HYPER_POST) &&
@@ -1076,15 +1184,51 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
 
 int bnnp_finalize(const BnnpLaunch* a, void* stream) {
     if (a == nullptr) return fail(BNNP_E_ARG, "bnnp_finalize: null args");
-    if (!a->pending.valid) return 0;
+    if (a->ctl == nullptr && !a->pending.valid) return 0;
     if (a->nseg <= 0 || a->segs == nullptr || a->seg_state == nullptr || a->partials == nullptr || a->stamps == nullptr)
         return fail(BNNP_E_ARG, "bnnp_finalize: null table pointer");
-    if ((a->pending.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)) && a->P == nullptr)
+    if (a->ctl == nullptr && (a->pending.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)) && a->P == nullptr)
         return fail(BNNP_E_ARG, "bnnp_finalize: the epilogue of a BNNP_F_HYPER / BNNP_F_HYPER_POST launch reads P");
-    if ((a->pending.parity | 1) != 1) return fail(BNNP_E_ARG, "bnnp_finalize: parity must be 0 or 1");
+    if (a->ctl == nullptr && (a->pending.parity | 1) != 1) return fail(BNNP_E_ARG, "bnnp_finalize: parity must be 0 or 1");
     bnnp_finalize_kernel<<<a->nseg, THREADS, 0, (cudaStream_t)stream>>>(*a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "bnnp_finalize_kernel launch");
+    return 0;
+}
+
+int bnnp_advance(const BnnpLaunch* a, void* stream) {
+    if (a == nullptr || a->ctl == nullptr) return fail(BNNP_E_ARG, "bnnp_advance: no control block");
+    if (a->coef_slot < 0 || a->coef_slot >= BNNP_COEF_SLOTS) return fail(BNNP_E_ARG, "bnnp_advance: coef_slot out of range");
+    bnnp_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a->ctl, a->op, a->phase, a->flags, a->coef_slot);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "bnnp_advance_kernel launch");
+    return 0;
+}
+
+int bnnp_clear_pending(BnnpControl* ctl, void* stream) {
+    if (ctl == nullptr) return fail(BNNP_E_ARG, "bnnp_clear_pending: no control block");
+    bnnp_clear_pending_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ctl);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "bnnp_clear_pending_kernel launch");
+    return 0;
+}
+
+int bnnp_poke(void* dst, const void* src_host, int64_t nbytes, void* stream) {
+    if (dst == nullptr || src_host == nullptr || nbytes <= 0 || nbytes % 4 != 0 || nbytes > 3840 ||
+        ((uintptr_t)dst & 3u) != 0)
+        return fail(BNNP_E_ARG, "bnnp_poke: need 0 < nbytes <= 3840, a multiple of 4, and a 4-byte aligned destination");
+    const int nwords = (int)(nbytes / 4);
+    if (nwords <= 64) {
+        PokePayload<64> pl;
+        memcpy(pl.w, src_host, (size_t)nbytes);
+        bnnp_poke_kernel<64><<<1, 64, 0, (cudaStream_t)stream>>>((uint32_t*)dst, pl, nwords);
+    } else {
+        PokePayload<960> pl;
+        memcpy(pl.w, src_host, (size_t)nbytes);
+        bnnp_poke_kernel<960><<<1, 256, 0, (cudaStream_t)stream>>>((uint32_t*)dst, pl, nwords);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "bnnp_poke_kernel launch");
     return 0;
 }
 

@@ -13,6 +13,7 @@ torch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes as C
+import operator
 import os
 import weakref
 from typing import List, Optional, Sequence
@@ -25,8 +26,17 @@ from .. import _native as N
 # BNNP_NVTX=1: an NVTX range around every launch (names the op / phase / flags in an nsys or ncu timeline)
 _NVTX = os.environ.get("BNNP_NVTX", "0") == "1"
 
+_GRAD = operator.attrgetter("grad")
+_VERSION = operator.attrgetter("_version")
+_DATA_PTR = torch.Tensor.data_ptr
+_IS = operator.is_
+_NO_MISSING: List[int] = []
+
 # keys of optimizer.state[p] whose values live on the device between launches
 LAZY_SCALARS = ("est_temperature", "est_config_temp", "delta_energy", "prev_new_momentum_delta")
+
+
+_NO_PENDING = (0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0)
 
 
 class SegState(dict):
@@ -124,8 +134,9 @@ class SegState(dict):
 class FlatGroup:
     """One param group of one chain in HBM."""
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], seed: int, stream_id: int):
+    def __init__(self, params: Sequence[torch.nn.Parameter], seed: int, stream_id: int, capturable: bool = False):
         self.params: List[torch.nn.Parameter] = list(params)
+        self.capturable = bool(capturable)
         if not self.params:
             raise ValueError("empty parameter group")
         dev = self.params[0].device
@@ -173,6 +184,14 @@ class FlatGroup:
         self.g_views = [self.G[o:o + n].view(p.shape) for o, n, p in zip(self.off, self.numel, self.params)]
         self.m_views: Optional[List[torch.Tensor]] = None
         self._p_ptrs = [v.data_ptr() for v in self.p_views]
+        self._gv_ptrs = [v.data_ptr() for v in self.g_views]
+        # per-segment gradient pointers (BnnpLaunch.seg_grad): a segment's gradient is read where it
+        # lies -- its slice of G, or the tensor autograd handed over after zero_grad() -- and this
+        # small device table is rewritten (bnnp_poke) only when one of the addresses changed
+        self.seg_grad_dev = torch.zeros(self.nseg, dtype=torch.int64, device=dev)
+        self._g_ptrs: List[int] = []                  # what the device table holds
+        self._held_grads: Optional[list] = None       # the p.grad tensors of the last sync (dropped by zero_grad)
+        self._gg_sig = None                           # (grad tensors, their versions) SUM_GG describes
 
         # per-segment scalars (BNNP_S_*) on the device, mirrored on demand
         self.state_dev = torch.zeros(self.nseg, N.STATE_STRIDE, dtype=torch.float64, device=dev)
@@ -184,6 +203,10 @@ class FlatGroup:
         self.partials = torch.zeros(2 * self.nchunks * N.NRED, dtype=torch.float64, device=dev)
         self.stamps = torch.zeros(2 * self.nchunks, dtype=torch.int64, device=dev)
         self._parity = 0
+        # capturable mode: call / parity / pending / coefficients live in a device control block
+        # (include/bnnp.h BnnpControl) and every launch is followed by bnnp_advance
+        self.ctl_dev = torch.zeros(C.sizeof(N.BnnpControl), dtype=torch.uint8, device=dev) if self.capturable else None
+        self._slot_cache = [None] * N.COEF_SLOTS      # coefficients each control-block slot holds
         self._pending = None     # epilogue parameters of the last launch, not yet applied to state_dev
         self._epoch = 0          # bumped by every launch / poke
         self._host_epoch = 0     # epoch state_host corresponds to
@@ -207,19 +230,21 @@ class FlatGroup:
         self._hyper_valid = False
         self._hyper_pversion = None
         # validity of SUM_GG / SUM_MM in the segment state
-        self._gg_version = None
         self._mm_version = None
 
         self._mom_published = False
-        self._tables_set = False
         self.serpentine = os.environ.get("BNNP_SERPENTINE", "1") != "0"
         self.seg_states = [SegState(self, i) for i in range(self.nseg)]
-        self._sync_rows = list(zip(self.params, self.g_views, self.p_views, self._p_ptrs))
         self._g_seen: List[Optional[tuple]] = [None] * self.nseg     # per tensor: (weakref to the foreign grad tensor, its version) last copied into G, or "zero"
         self.args = N.BnnpLaunch()
+        self._argbuf = (C.c_char * C.sizeof(N.BnnpLaunch)).from_buffer(self.args)
+        self._static_dirty = True        # pointer fields of self.args need a refresh
+        self._var_ptrs = None            # (prev_m, replay_noise, chunk_ids) now in self.args
         self.launches = 0
+        self.copies = 0                  # gradients that had to be copied into G (not readable in place)
 
         self.adopt_parameters()
+        self._write_grad_table(list(self._gv_ptrs))
 
     # ------------------------------------------------------------------ views
     @torch.no_grad()
@@ -233,56 +258,98 @@ class FlatGroup:
                 self.g_views[i].copy_(p.grad)
                 p.grad = self.g_views[i]
 
-    @torch.no_grad()
     def sync_views(self, raise_on_no_grad: bool) -> List[int]:
-        """Bring the flat arrays up to date with what the model holds: a p.grad that is
-        not the flat view (after `zero_grad()` autograd stores every gradient in a tensor
-        of its own) is copied into G -- all of them with one multi-tensor copy --, a
-        parameter whose storage was swapped (`Prior.sample()`) is re-adopted.  Returns the
-        indices of parameters that have no gradient (sgld.py:96-101)."""
+        """Make the launch arguments describe what the model holds now.  Gradients are read IN PLACE:
+        after `zero_grad()` autograd stores every gradient in a tensor of its own, and the kernel
+        reads it there through the per-segment pointer table (BnnpLaunch.seg_grad) -- the table is
+        rewritten only when an address changed (in a steady training loop the caching allocator
+        hands back the same blocks, so: never).  A parameter whose storage was swapped
+        (`Prior.sample()`) is re-adopted.  Returns the indices of parameters that have no gradient
+        (sgld.py:96-101)."""
+        grads = list(map(_GRAD, self.params))
+        try:
+            ptrs = list(map(_DATA_PTR, grads))
+        except TypeError:                      # a parameter without gradient
+            ptrs = None
+        missing = _NO_MISSING
+        if ptrs != self._g_ptrs:
+            missing = self._sync_grads_slow(grads, raise_on_no_grad)
+        self._held_grads = grads
+        if list(map(_DATA_PTR, self.params)) != self._p_ptrs:
+            self._readopt_parameters()
+        return missing
+
+    @torch.no_grad()
+    def _sync_grads_slow(self, grads, raise_on_no_grad: bool) -> List[int]:
         missing: List[int] = []
+        new_ptrs = list(self._g_ptrs)
         dst: List[torch.Tensor] = []
         src: List[torch.Tensor] = []
-        i = 0
-        for p, gv, pv, ptr in self._sync_rows:
-            g = p.grad
-            if g is not gv:
-                if g is None and i in self.hyper_links:
+        for i, g in enumerate(grads):
+            gv = self.g_views[i]
+            if g is gv:
+                new_ptrs[i] = self._gv_ptrs[i]
+            elif g is None:
+                if i in self.hyper_links:
                     # a fused hyper-parameter reaches the loss only through the prior, which is no
-                    # longer in autograd: its likelihood gradient is zero.  Its slot of G is zeroed
-                    # once and stays zero as long as nobody hands a gradient over (no launch, no
-                    # re-binding per step)
+                    # longer in autograd: its likelihood gradient is zero.  p.grad becomes the (zeroed)
+                    # flat view, so that runner code that touches every p.grad (the clamp loop of
+                    # inference.py:219-220) keeps working
                     if self._g_seen[i] != "zero":
                         gv.zero_()
                         self._g_seen[i] = "zero"
-                elif g is None:
-                    if raise_on_no_grad:
-                        raise RuntimeError(f"No gradient for parameter with shape {p.shape}")
-                    missing.append(i)
+                    self.params[i].grad = gv
+                    grads[i] = gv
+                    new_ptrs[i] = self._gv_ptrs[i]
+                elif raise_on_no_grad:
+                    raise RuntimeError(f"No gradient for parameter with shape {self.params[i].shape}")
                 else:
-                    # a gradient autograd put into a tensor of its own (the usual case after
-                    # zero_grad(): p.grad was None and backward() stored its buffer there).  Copied
-                    # once: the same tensor at the same version is already in G, and G must not look
-                    # modified (with a fused prior the sums of the last step cannot be recomputed
-                    # once P has moved: the reference's p.grad holds the prior gradient at the OLD p)
-                    seen = self._g_seen[i]
-                    ver = g._version
-                    if seen is None or seen == "zero" or seen[0]() is not g or seen[1] != ver:
-                        dst.append(gv)
-                        src.append(g)
-                        self._g_seen[i] = (weakref.ref(g), ver)    # weak: the old gradient may be freed
-            if p.data_ptr() != ptr:
-                pv.copy_(p.data)
-                p.data = pv
-                self._lp_valid = self._hyper_valid = False
-            i += 1
+                    missing.append(i)
+            elif (g.dtype is torch.float32 and g.device == self.device and g.layout is torch.strided
+                  and g.is_contiguous() and g.numel() == self.numel[i] and (g.data_ptr() & 15) == 0):
+                new_ptrs[i] = g.data_ptr()          # read where it lies
+                self._g_seen[i] = None
+            else:
+                # not readable in place (other dtype / device / layout, unaligned): copied into G, once
+                # per tensor and version
+                seen = self._g_seen[i]
+                ver = g._version
+                if seen is None or seen == "zero" or seen[0]() is not g or seen[1] != ver:
+                    dst.append(gv)
+                    src.append(g)
+                    self._g_seen[i] = (weakref.ref(g), ver)
+                new_ptrs[i] = self._gv_ptrs[i]
         if dst:
+            self.copies += len(dst)
             try:
                 torch._foreach_copy_(dst, src)      # one multi-tensor launch instead of one copy per tensor
             except (RuntimeError, TypeError):
                 for d, g in zip(dst, src):
                     d.copy_(g)
+        if new_ptrs != self._g_ptrs:
+            self._write_grad_table(new_ptrs)
         return missing
+
+    def _write_grad_table(self, ptrs: List[int]) -> None:
+        "device table of gradient addresses <- ptrs (stream-ordered, through kernel parameters: bnnp_poke)"
+        arr = np.asarray(ptrs, dtype=np.int64)
+        base = self.seg_grad_dev.data_ptr()
+        with torch.cuda.device(self.device):
+            stream = self._stream()
+            for lo in range(0, self.nseg, 480):
+                part = np.ascontiguousarray(arr[lo:lo + 480])
+                N.check(self.lib.bnnp_poke(base + 8 * lo, part.ctypes.data, part.nbytes, stream), "bnnp_poke")
+        self._g_ptrs = list(ptrs)
+        self.launches += (self.nseg + 479) // 480
+        self.table_writes = getattr(self, "table_writes", 0) + 1
+
+    @torch.no_grad()
+    def _readopt_parameters(self) -> None:
+        for i, (p, pv) in enumerate(zip(self.params, self.p_views)):
+            if p.data_ptr() != self._p_ptrs[i]:
+                pv.copy_(p.data)
+                p.data = pv
+                self._lp_valid = self._hyper_valid = False
 
     def bind_grad_views(self) -> None:
         "p.grad <- its view of the flat G array, for every parameter"
@@ -290,11 +357,26 @@ class FlatGroup:
             if p.grad is not v:
                 p.grad = v
         self._g_seen = [None] * self.nseg
+        self._held_grads = None
+
+    def drop_grads(self) -> None:
+        "zero_grad(set_to_none=True): p.grad = None (a fused hyper-parameter keeps its zero view)"
+        for p in self.params:
+            p.grad = None
+        for i in self.hyper_links:
+            if self.prior_fused:
+                if self._g_seen[i] != "zero":
+                    self.g_views[i].zero_()
+                    self._g_seen[i] = "zero"
+                self.params[i].grad = self.g_views[i]
+        self._held_grads = None
+        self._gg_sig = None
 
     def ensure_momentum_storage(self) -> None:
         if self.M is None:
             self.M = torch.zeros(self.total, dtype=torch.float32, device=self.device)
             self._ptrs["M"] = self.M.data_ptr()
+            self._static_dirty = True
             self.m_views = [self.M[o:o + n].view(p.shape) for o, n, p in zip(self.off, self.numel, self.params)]
 
     def set_momentum(self, i: int, value: torch.Tensor) -> torch.Tensor:
@@ -327,12 +409,14 @@ class FlatGroup:
             self.prev_p = torch.zeros_like(self.P)
             self.prev_g = torch.zeros_like(self.P)
             self._ptrs["prev_p"], self._ptrs["prev_g"] = self.prev_p.data_ptr(), self.prev_g.data_ptr()
+            self._static_dirty = True
             for s, o, n, p in zip(self.seg_states, self.off, self.numel, self.params):
                 s.raw_set("prev_parameter", self.prev_p[o:o + n].view(p.shape))
                 s.raw_set("prev_grad", self.prev_g[o:o + n].view(p.shape))
         if with_momentum and self.prev_m is None:
             self.prev_m = torch.zeros_like(self.P)
             self._ptrs["prev_m"] = self.prev_m.data_ptr()
+            self._static_dirty = True
             for s, o, n, p in zip(self.seg_states, self.off, self.numel, self.params):
                 s.raw_set("prev_momentum_buffer", self.prev_m[o:o + n].view(p.shape))
 
@@ -446,7 +530,7 @@ class FlatGroup:
     def fetch(self) -> np.ndarray:
         """Host mirror of the segment-state array (one D2H copy + one stream sync,
         only if a launch happened since the last fetch)."""
-        if self._host_epoch != self._epoch:
+        if self._host_epoch != self._epoch or self.capturable:     # (graph replays launch behind the host's back)
             self.flush_pending()
             self.state_host.copy_(self.state_dev, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
@@ -454,7 +538,7 @@ class FlatGroup:
         return self.state_np
 
     def materialize(self) -> None:
-        if self._mat_epoch == self._epoch:
+        if self._mat_epoch == self._epoch and not self.capturable:
             return
         st = self.fetch()
         nd = self.metrics_num_data
@@ -479,46 +563,66 @@ class FlatGroup:
     def _stream(self) -> int:
         return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
-    def _table_pointers(self, a) -> None:
-        if self._tables_set:
-            return
+    def _refresh_static(self) -> None:
+        "the pointer / size fields of the launch block that only change when storage is (re)allocated"
+        a, ptr = self.args, self._ptrs
+        a.P, a.G, a.M = ptr["P"], ptr["G"], ptr.get("M")
+        a.prev_p, a.prev_g = ptr.get("prev_p"), ptr.get("prev_g")
         a.segs, a.chunks = self.table_dev.data_ptr(), self.chunks_dev.data_ptr()
+        a.seg_grad = self.seg_grad_dev.data_ptr()
+        a.ctl = self.ctl_dev.data_ptr() if self.capturable else None
         a.seg_state, a.partials, a.stamps = self.state_dev.data_ptr(), self.partials.data_ptr(), self.stamps.data_ptr()
-        a.nseg, a.nchunks_total = self.nseg, self.nchunks
-        self._tables_set = True
+        a.nseg = self.nseg
+        self._var_ptrs = None
+        self._static_dirty = False
 
-    def _set_pending(self, a) -> None:
-        e, pend = a.pending, self._pending
-        if pend is None:
-            e.valid = 0
-        else:
-            (e.valid, e.op, e.phase, e.flags, e.parity, e.call,
-             e.c_gm_base, e.curv_base, e.rms_alpha, e.inv_num_data) = (1,) + pend
-
-    def _issue(self, a) -> None:
-        """bnnp_launch with this chain's deferred-epilogue protocol: the launch carries the
-        previous launch's epilogue (applied on the device by the first-chunk CTA of every
-        segment) and leaves its own pending."""
-        self._set_pending(a)
-        a.parity, a.call = self._parity, self.call
-        if self.serpentine:
-            # alternate the chunk order from launch to launch: each launch starts on the lines the
-            # previous one left in L2 (include/bnnp.h: BNNP_F_REVERSE)
-            a.flags = (a.flags | N.F_REVERSE) if self._parity else (a.flags & ~N.F_REVERSE)
-        if _NVTX:
-            torch.cuda.nvtx.range_push(f"bnnp_launch op={a.op} phase={a.phase} flags={a.flags:#x}")
+    def _call_lib(self, fn, what: str) -> None:
         if torch.cuda.current_device() != self._dev_index:
             with torch.cuda.device(self.device):
-                rc = self.lib.bnnp_launch(C.byref(a), self._stream())
+                rc = fn(C.byref(self.args), self._stream())
         else:
-            rc = self.lib.bnnp_launch(C.byref(a), self._stream())
+            rc = fn(C.byref(self.args), self._stream())
+        if rc != 0:
+            N.check(rc, what)
+
+    def _issue(self, nchunks, op, phase, noise, flags, cm, cg, cn, cp, inv_n, c_gm_base, curv_base, rms_alpha) -> None:
+        """bnnp_launch with this chain's deferred-epilogue protocol: the launch carries the
+        previous launch's epilogue (applied on the device by the first-chunk CTA of every
+        segment) and leaves its own pending.  The part of the argument block that changes from
+        launch to launch is written with one struct.pack_into."""
+        parity, call = self._parity, self.call
+        if self.serpentine and parity:
+            # alternate the chunk order from launch to launch: each launch starts on the lines the
+            # previous one left in L2 (include/bnnp.h: BNNP_F_REVERSE)
+            flags |= N.F_REVERSE
+        else:
+            flags &= ~N.F_REVERSE
+        slot = 0
+        if self.capturable:
+            slot = phase if op <= N.OP_HMC else N.SLOT_OTHER
+            self.poke_coef(slot, (cm, cg, cn, cp, inv_n, c_gm_base, curv_base, rms_alpha))
+            pend = _NO_PENDING
+        else:
+            pend = self._pending or _NO_PENDING
+        gmax = self.grad_max if self.grad_max is not None else 0.0
+        N.DYN_STRUCT.pack_into(self._argbuf, N.DYN_OFFSET,
+                               nchunks, self.nchunks, parity, op, phase, noise, flags, slot, 0,
+                               self.key[0], self.key[1], call,
+                               cm, cg, cn, cp, inv_n, gmax, c_gm_base, curv_base, rms_alpha, *pend)
+        if _NVTX:
+            torch.cuda.nvtx.range_push(f"bnnp_launch op={op} phase={phase} flags={flags:#x}")
+        self._call_lib(self.lib.bnnp_launch, "bnnp_launch")
+        if self.capturable:
+            self._call_lib(self.lib.bnnp_advance, "bnnp_advance")
+            self._pending = True
+            self.launches += 1
+        else:
+            self._pending = (1, op, phase, flags, parity, 0, call, c_gm_base, curv_base, rms_alpha, inv_n)
         if _NVTX:
             torch.cuda.nvtx.range_pop()
-        N.check(rc, "bnnp_launch")
-        self._pending = (a.op, a.phase, a.flags, self._parity, self.call, a.c_gm_base, a.curv_base, a.rms_alpha,
-                         a.inv_num_data)
-        self._parity ^= 1
-        self.call += 1
+        self._last_issue = (nchunks, op, phase, noise, flags, cm, cg, cn, cp, inv_n, c_gm_base, curv_base, rms_alpha)
+        self._parity = parity ^ 1
+        self.call = call + 1
         self._epoch += 1
         self.launches += 1
 
@@ -526,17 +630,21 @@ class FlatGroup:
         """Apply the last launch's per-segment bookkeeping to state_dev now (bnnp_finalize).
         Needed before the host reads state_dev, before the segment table changes and before a
         launch that skips segments; a plain sequence of steps never calls it."""
-        if self._pending is None:
+        if self._pending is None and not self.capturable:
             return
-        a = self.args
-        self._table_pointers(a)
-        self._set_pending(a)
-        if torch.cuda.current_device() != self._dev_index:
+        if self._static_dirty:
+            self._refresh_static()
+        if self.capturable:
+            # the pending epilogue is in the control block; after graph replays the host does not even
+            # know whether there is one: the finalize kernel looks, bnnp_clear_pending marks it done
+            self._call_lib(self.lib.bnnp_finalize, "bnnp_finalize")
             with torch.cuda.device(self.device):
-                rc = self.lib.bnnp_finalize(C.byref(a), self._stream())
-        else:
-            rc = self.lib.bnnp_finalize(C.byref(a), self._stream())
-        N.check(rc, "bnnp_finalize")
+                N.check(self.lib.bnnp_clear_pending(self.ctl_dev.data_ptr(), self._stream()), "bnnp_clear_pending")
+            self.launches += 2
+            self._pending = None
+            return
+        N.PENDING_STRUCT.pack_into(self._argbuf, N.BnnpLaunch.pending.offset, *self._pending)
+        self._call_lib(self.lib.bnnp_finalize, "bnnp_finalize")
         self._pending = None
         self.launches += 1
 
@@ -547,35 +655,43 @@ class FlatGroup:
             self.flush_pending()      # every segment's pending epilogue needs a CTA; a partial launch has none for some
         if self._table_dirty:
             self._upload_table()
+        if self._static_dirty:
+            self._refresh_static()
         a = self.args
         chunk_ids, nchunks = chunks if chunks is not None else (None, self.nchunks)
-        ptr = self._ptrs
-        a.P, a.G, a.M = ptr["P"], ptr["G"], ptr.get("M")
-        a.prev_p, a.prev_g = ptr.get("prev_p"), ptr.get("prev_g")
-        a.prev_m = ptr.get("prev_m") if (flags & N.F_READ_M) else None
+        replay = None
         if noise == N.NOISE_REPLAY:
             if self.replay is None:
                 raise RuntimeError("replay noise requested but none was provided")
-            a.replay_noise = self.replay.data_ptr()
-        else:
-            a.replay_noise = None
-        self._table_pointers(a)
-        a.chunk_ids = chunk_ids.data_ptr() if chunk_ids is not None else None
+            replay = self.replay.data_ptr()
+        var = (self._ptrs.get("prev_m") if (flags & N.F_READ_M) else None, replay,
+               chunk_ids.data_ptr() if chunk_ids is not None else None)
+        if var != self._var_ptrs:
+            a.prev_m, a.replay_noise, a.chunk_ids = var
+            self._var_ptrs = var
         self._chunk_ids_keepalive = chunk_ids
-        a.nchunks = nchunks
-        a.op, a.phase, a.noise, a.flags = op, phase, noise, flags
-        a.key0, a.key1 = self.key[0], self.key[1]
-        a.cm, a.cg, a.cn, a.cp = cm, cg, cn, cp
-        a.inv_num_data = inv_num_data
-        a.grad_max = self.grad_max if self.grad_max is not None else 0.0
-        a.c_gm_base, a.curv_base, a.rms_alpha = c_gm_base, curv_base, rms_alpha
-        self._issue(a)
+        self._issue(nchunks, op, phase, noise, flags, cm, cg, cn, cp, inv_num_data, c_gm_base, curv_base, rms_alpha)
+
+    def launch_coef(self, op: int, phase: int, flags: int, noise: int, coef, chunks=None) -> None:
+        "launch() with the coefficients as the 8-tuple of a BnnpCoef (the samplers' `_coefs`)"
+        cm, cg, cn, cp, inv_n, c_gm_base, curv_base, rms_alpha = coef
+        self.launch(op, phase, flags, noise, cm, cg, cn, cp, inv_n, c_gm_base, curv_base, rms_alpha, chunks)
+
+    def poke_coef(self, slot: int, coef) -> None:
+        "capturable mode: coefficient slot `slot` of the device control block <- coef (if it differs)"
+        if self._slot_cache[slot] == tuple(coef):
+            return
+        raw = N.COEF_STRUCT.pack(*coef)
+        dst = self.ctl_dev.data_ptr() + N.BnnpControl.coef.offset + slot * N.COEF_STRUCT.size
+        with torch.cuda.device(self.device):
+            N.check(self.lib.bnnp_poke(dst, raw, len(raw), self._stream()), "bnnp_poke")
+        self._slot_cache[slot] = tuple(coef)
+        self.launches += 1
 
     def relaunch(self) -> None:
-        """Launch again with the argument block of the previous launch (same
-        coefficients, next Philox counter): the C-ABI-level hot loop that bench.py
-        times for the device-resident number."""
-        self._issue(self.args)
+        """Launch again with the arguments of the previous launch (same coefficients, next Philox
+        counter): the C-ABI-level hot loop that bench.py times for the device-resident number."""
+        self._issue(*self._last_issue)
 
     def chunks_without(self, missing: Sequence[int]):
         """(device list of chunk indices, count) that skips the segments in `missing`
@@ -596,12 +712,19 @@ class FlatGroup:
     def _p_version(self) -> int:
         return sum(p._version for p in self.params)
 
-    def note_step_sums(self, flags: int, op: int) -> None:
-        """Called after a step launch: SUM_GG in the segment state now describes G
-        (the gradient the step used); SUM_MM describes M as stored if the launch
-        reduced every sum; LOG_PRIOR describes P as stored if it carried
-        BNNP_F_LOG_PRIOR."""
-        self._gg_version = self.G._version
+    def note_step_sums(self, flags: int, op: int, capture_grads: bool = True) -> None:
+        """Called after a step launch: SUM_GG in the segment state now describes the gradient the
+        step used (remembered as the p.grad tensors and their versions, if `capture_grads`); SUM_MM
+        describes M as stored if the launch reduced every sum; LOG_PRIOR describes P as stored if
+        it carried BNNP_F_LOG_PRIOR."""
+        held = self._held_grads
+        if capture_grads and held is not None:
+            try:
+                self._gg_sig = (held, list(map(_VERSION, held)))
+            except AttributeError:             # a parameter without gradient was skipped
+                self._gg_sig = None
+        else:
+            self._gg_sig = None
         all_sums = bool(flags & (N.F_CALC_METRICS | N.F_ALL_SUMS)) or op in (N.OP_SAMPLE_MOMENTUM, N.OP_REDUCE)
         self._mm_version = self.M._version if (self.M is not None and all_sums) else None
         if flags & N.F_LOG_PRIOR:
@@ -613,11 +736,12 @@ class FlatGroup:
             self._hyper_valid = False
 
     def invalidate_sums(self) -> None:
-        self._gg_version = self._mm_version = None
+        self._gg_sig = self._mm_version = None
         self._lp_valid = self._hyper_valid = False
 
     def reduce_now(self, inv_num_data: float) -> None:
-        """dot(g,g), dot(m,m) and the log-prior of the CURRENT arrays (no writes)."""
+        """dot(g,g), dot(m,m) and the log-prior of the CURRENT arrays (no writes).  The caller has
+        just run sync_views(raise_on_no_grad=True): every gradient pointer is current."""
         flags = N.F_READ_G
         if self.M is not None:
             flags |= N.F_READ_M
@@ -632,14 +756,24 @@ class FlatGroup:
             if self.clamp_active:
                 flags |= N.F_CLAMP_GRAD
         self.launch(N.OP_REDUCE, N.PHASE_MID, flags, N.NOISE_NONE, cm=1.0, inv_num_data=inv_num_data)
-        self._gg_version = self.G._version
+        self.note_step_sums(flags, N.OP_REDUCE)
         self._mm_version = self.M._version if self.M is not None else None
-        if self.prior_fused and not self.has_hyper:
-            self._lp_valid = True
-            self._lp_pversion = self._p_version()
+
+    def reduce_log_prior(self, inv_num_data: float) -> None:
+        """sum log p(theta) of the parameters now in P, nothing else: reads P only (4 B/param), so it
+        is also legal while the gradients are gone (model.log_prior() right after zero_grad(),
+        inference_reject.py:19-20)."""
+        self.launch(N.OP_REDUCE, N.PHASE_MID, N.F_READ_P | N.F_LOG_PRIOR, N.NOISE_NONE, cm=1.0,
+                    inv_num_data=inv_num_data)
+        self._lp_valid = True
+        self._lp_pversion = self._p_version()
 
     def sums_fresh(self, need_mm: bool) -> bool:
-        if self._gg_version is None or self._gg_version != self.G._version:
+        sig = self._gg_sig
+        if sig is None:
+            return False
+        cur = list(map(_GRAD, self.params))
+        if len(cur) != len(sig[0]) or not all(map(_IS, cur, sig[0])) or list(map(_VERSION, cur)) != sig[1]:
             return False
         if need_mm and (self.M is None or self._mm_version != self.M._version):
             return False

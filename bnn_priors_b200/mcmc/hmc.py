@@ -29,10 +29,10 @@ class HMC(VerletSGLD):
     def __init__(self, params: Sequence[Union[torch.nn.Parameter, Dict]],
                  lr: float, num_data: int,
                  raise_on_no_grad: bool = True, raise_on_nan: bool = True,
-                 *, seed: Optional[int] = None, chain: int = 0):
+                 *, seed: Optional[int] = None, chain: int = 0, capturable: bool = False):
         super().__init__(params, lr, num_data, 1., 1.,
                          raise_on_no_grad=raise_on_no_grad,
-                         raise_on_nan=raise_on_nan, seed=seed, chain=chain)
+                         raise_on_nan=raise_on_nan, seed=seed, chain=chain, capturable=capturable)
 
     def _point_energy_i(self, group, fg: FlatGroup, i: int) -> float:
         "hmc.py:32-33: .5 * dot(momentum, momentum) of the momentum now stored"
@@ -42,6 +42,10 @@ class HMC(VerletSGLD):
         # whatever a runner or scheduler wrote into the group, HMC is a = 1, T = 1 (hmc.py:35-39)
         super()._update_group_fn(g, phase=phase)
         assert g['momentum'] == 1. and g['temperature'] == 1.
+
+    def _coefs(self, group, fg: FlatGroup, phase: int):
+        inv_n = 1.0 / group['num_data'] if fg.prior_fused else 0.0
+        return (1.0, -.5 * group['grad_v'] * group['bhn'], 0.0, group['bh'], inv_n, 0.0, 0.0, group['rmsprop_alpha'])
 
     def _step_fn(self, group, fg: FlatGroup, chunks, is_initial=False, is_final=False,
                  save_state=False, calc_metrics=True):
@@ -61,14 +65,13 @@ class HMC(VerletSGLD):
         if not is_final:
             flags |= N.F_WRITE_P | N.F_UPDATE_SQ
             flags |= fg.step_prior_flags(pf, chunks)
-        fg.launch(self._OP, self._phase(is_initial, is_final), flags, N.NOISE_NONE,
-                  cm=1.0, cg=-.5 * group['grad_v'] * group['bhn'], cn=0.0, cp=group['bh'],
-                  inv_num_data=inv_n, rms_alpha=group['rmsprop_alpha'], chunks=chunks)
+        phase = self._phase(is_initial, is_final)
+        fg.launch_coef(self._OP, phase, flags, N.NOISE_NONE, self._coefs(group, fg, phase), chunks)
         if calc_metrics:
             fg.have_metrics = True
             fg.metrics_num_data = group['num_data']
         if is_initial:
             fg.have_delta = True
-        fg.note_step_sums(flags, self._OP)
+        fg.note_step_sums(flags, self._OP, capture_grads=(is_initial or is_final or calc_metrics))
         if flags & N.F_HYPER_POST:
             fg.after_hyper_post()

@@ -8,6 +8,8 @@ instead of ~7 eager ops and 2-4 `.item()` syncs per tensor.
 from __future__ import annotations
 
 import math
+import sys
+import weakref
 from collections import OrderedDict
 from typing import Callable, Dict, Optional, Sequence, Union
 
@@ -15,6 +17,18 @@ import torch
 
 from .. import _native as N
 from ._flat import FlatGroup
+
+
+_OPT_MOD = sys.modules[torch.optim.Optimizer.__module__]      # torch.optim.optimizer (global step hooks)
+_PROFILER = torch.autograd.profiler
+
+
+_LIVE = weakref.WeakSet()
+
+
+def live_samplers():
+    "the samplers of this process that are still alive (sample_sink.FlatSampleSaver finds its chain here)"
+    return list(_LIVE)
 
 
 def dot(a, b):
@@ -38,7 +52,10 @@ class SGLD(torch.optim.Optimizer):
         raise_on_nan      a non-finite gradient raises ValueError
 
     Engine-only extras (keyword-only, not in the reference): `seed` / `chain` pick
-    the Philox stream of the in-kernel noise (default: torch.initial_seed(), 0).
+    the Philox stream of the in-kernel noise (default: torch.initial_seed(), 0);
+    `capturable=True` keeps the launch state (Philox counter, walking direction, pending
+    bookkeeping, coefficients) in device memory, so that steps can be recorded in a CUDA graph
+    together with the forward / backward pass and replayed.
     """
     _OP = N.OP_SGLD
 
@@ -46,7 +63,7 @@ class SGLD(torch.optim.Optimizer):
                  num_data: int, momentum: float = 0, temperature: float = 1.,
                  rmsprop_alpha: float = 0.99, rmsprop_eps: float = 1e-8,
                  raise_on_no_grad: bool = True, raise_on_nan: bool = False,
-                 *, seed: Optional[int] = None, chain: int = 0):
+                 *, seed: Optional[int] = None, chain: int = 0, capturable: bool = False):
         assert lr >= 0 and num_data >= 0 and momentum >= 0 and temperature >= 0
         defaults = dict(lr=lr, num_data=num_data, momentum=momentum,
                         rmsprop_alpha=rmsprop_alpha, rmsprop_eps=rmsprop_eps,
@@ -56,13 +73,15 @@ class SGLD(torch.optim.Optimizer):
         self.raise_on_nan = raise_on_nan
         if seed is None:
             seed = torch.initial_seed()
-        self._flat = [FlatGroup(g['params'], seed, (chain << 16) + gi)
+        self.capturable = bool(capturable)
+        self._flat = [FlatGroup(g['params'], seed, (chain << 16) + gi, capturable=self.capturable)
                       for gi, g in enumerate(self.param_groups)]
         for fg in self._flat:
             for p, s in zip(fg.params, fg.seg_states):
                 self.state[p] = s
         self.update_preconditioner()
         self._step_count = 0  # keep the `torch.optim.scheduler` happy
+        _LIVE.add(self)
 
     def add_param_group(self, param_group):
         """Groups are laid out in HBM when the sampler is constructed (the reference's runners pass
@@ -102,16 +121,72 @@ class SGLD(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True):
         """inference.py:216 calls this every minibatch.  Like torch >= 2's default it drops the
         gradients (`p.grad = None`): backward() then hands every gradient over in a fresh tensor
-        without an accumulation kernel, and the next sampler call copies all of them into the flat
-        G array with one multi-tensor copy (FlatGroup.sync_views).  `set_to_none=False` zeroes G
-        with one memset and binds p.grad to its views, so that autograd accumulates in place."""
+        without an accumulation kernel, and the next sampler call reads those tensors where they
+        lie (FlatGroup.sync_views: per-segment gradient pointers, no copy).  `set_to_none=False`
+        zeroes G with one memset and binds p.grad to its views, so that autograd accumulates in
+        place."""
         for fg in self._flat:
             if set_to_none:
-                for p in fg.params:
-                    p.grad = None
+                fg.drop_grads()
             else:
                 fg.G.zero_()
                 fg.bind_grad_views()
+
+    # ------------------------------------------------------------------ torch.optim plumbing
+    def _patch_step_function(self) -> None:
+        """torch.optim.Optimizer wraps `step` in a profiler range plus pre / post hook dispatch,
+        which costs more host time than this sampler's whole step.  `step` below does the same
+        dispatch itself, but only when a hook is registered or a profiler is running."""
+        self._zero_grad_profile_name = f"Optimizer.zero_grad#{self.__class__.__name__}.zero_grad"
+
+    def _hooks_active(self) -> bool:
+        return bool(self._optimizer_step_pre_hooks or self._optimizer_step_post_hooks
+                    or _OPT_MOD._global_optimizer_pre_hooks or _OPT_MOD._global_optimizer_post_hooks
+                    or _PROFILER._is_profiler_enabled)
+
+    def _hooked(self, name, *args, **kwargs):
+        "the slow path: the method `name` under torch's profile_hook_step wrapper"
+        fn = torch.optim.Optimizer.profile_hook_step(getattr(type(self), "_" + name + "_impl"))
+        return fn(self, *args, **kwargs)
+
+    def state_dict(self):
+        """torch's state_dict plus `square_avg` (the engine keeps only its mean; written out as the
+        constant tensor with that mean, which is all `update_preconditioner` reads: sgld.py:170-173)."""
+        for fg in self._flat:
+            for i, s in enumerate(fg.seg_states):
+                s.raw_set('square_avg', fg.square_avg_tensor(i))
+        try:
+            return super().state_dict()
+        finally:
+            for fg in self._flat:
+                for s in fg.seg_states:
+                    dict.pop(s, 'square_avg', None)
+
+    def load_state_dict(self, state_dict):
+        """torch replaces `self.state[p]` by plain dicts; route the loaded values back into the flat
+        arrays / the device-side segment state (momentum_buffer, preconditioner, square_avg,
+        delta_energy, prev_*) and restore the lazy state dicts."""
+        super().load_state_dict(state_dict)
+        for fg in self._flat:
+            loaded_momentum = False
+            for p, s in zip(fg.params, fg.seg_states):
+                loaded = self.state.get(p)
+                if loaded is s:
+                    continue
+                self.state[p] = s
+                for k, v in (loaded or {}).items():
+                    if k in ('prev_parameter', 'prev_grad', 'prev_momentum_buffer'):
+                        fg.ensure_prev_storage(with_momentum=(k == 'prev_momentum_buffer'))
+                        with torch.no_grad():
+                            s.raw_get(k).copy_(v)
+                    elif k in ('est_temperature', 'est_config_temp'):
+                        continue              # diagnostics of the last step: recomputed by the next one
+                    else:
+                        s[k] = v
+                        loaded_momentum |= k == 'momentum_buffer'
+            if loaded_momentum:
+                fg.publish_momentum()
+            fg.invalidate_sums()
 
     def delta_energy(self, a, b) -> float:
         return math.inf
@@ -141,15 +216,20 @@ class SGLD(torch.optim.Optimizer):
             fg._mm_version = fg.M._version
 
     # ------------------------------------------------------------------ steps
-    @torch.no_grad()
-    def step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
-             calc_metrics=True, save_state=False):
+    def _step_impl(self, closure: Optional[Callable[..., torch.Tensor]] = None,
+                   calc_metrics=True, save_state=False):
         assert save_state is False
         return self._step_internal(self._update_group_fn, self._step_fn,
                                    closure, calc_metrics=calc_metrics)
+
+    def step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
+             calc_metrics=True, save_state=False):
+        if self._hooks_active():
+            return self._hooked("step", closure, calc_metrics=calc_metrics, save_state=save_state)
+        return self._step_impl(closure, calc_metrics, save_state)
+    step.hooked = True          # torch.optim.Optimizer: do not wrap again (see _patch_step_function)
     initial_step = step
 
-    @torch.no_grad()
     def final_step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
                    calc_metrics=True, save_state=False):
         assert save_state is False
@@ -164,20 +244,30 @@ class SGLD(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group, fg in zip(self.param_groups, self._flat):
-            update_group_fn(group)
-            missing = fg.sync_views(self.raise_on_no_grad)
-            chunks = None
-            if missing:
-                chunks = fg.chunks_without(missing)
-                if chunks is None:
-                    continue
-            step_fn(group, fg, chunks, **step_fn_kwargs)
-            if self.raise_on_nan:
-                self._raise_if_nonfinite(fg, missing)
+        grad_was_enabled = torch.is_grad_enabled()
+        torch._C._set_grad_enabled(False)
+        try:
+            for group, fg in zip(self.param_groups, self._flat):
+                update_group_fn(group)
+                missing = fg.sync_views(self.raise_on_no_grad)
+                chunks = None
+                if missing:
+                    chunks = fg.chunks_without(missing)
+                    if chunks is None:
+                        continue
+                if self.raise_on_nan:
+                    self._raise_if_nonfinite(fg, chunks, missing)
+                step_fn(group, fg, chunks, **step_fn_kwargs)
+        finally:
+            torch._C._set_grad_enabled(grad_was_enabled)
         return loss
 
-    def _raise_if_nonfinite(self, fg, missing=()):
+    def _raise_if_nonfinite(self, fg, chunks, missing=()):
+        """sgld.py:102-104: a non-finite gradient raises BEFORE anything is updated.  One read-only
+        launch over the gradients (4 B/param) + the read-back of the per-tensor flags; only with
+        `raise_on_nan=True` (HMC's default)."""
+        fg.launch(N.OP_REDUCE, N.PHASE_MID, N.F_READ_G, N.NOISE_NONE, cm=1.0, chunks=chunks)
+        fg.invalidate_sums()
         st = fg.fetch()
         for i, p in enumerate(fg.params):
             if i not in missing and st[i, N.S_NONFINITE] != 0.0:
@@ -202,6 +292,31 @@ class SGLD(torch.optim.Optimizer):
             fg.hyper_prepass(1.0 / group['num_data'])
         return f, 1.0 / group['num_data']
 
+    def _coefs(self, group, fg: FlatGroup, phase: int):
+        """(cm, cg, cn, cp, 1/N, c_gm_base, curv_base, rms_alpha) of a transition, from the derived
+        entries `_update_group_fn` left in the group (include/bnnp.h BnnpCoef)"""
+        a = group['momentum']
+        inv_n = 1.0 / group['num_data'] if fg.prior_fused else 0.0
+        if phase == N.PHASE_FINAL:
+            # no writes; m' = 1*m so that the sums describe the stored momentum
+            return (1.0 if a > 0 else 0.0, 0.0, 0.0, 0.0, inv_n, 0.0, 0.0, 0.0)
+        return (a, -group['hn'], group['noise_std'], group['h'], inv_n, 0.0, 0.0, group['rmsprop_alpha'])
+
+    def _update_group_for(self, group, phase: int) -> None:
+        self._update_group_fn(group)
+
+    def sync_hyperparameters(self) -> None:
+        """capturable=True: write the coefficients that follow from the CURRENT `param_groups`
+        (lr, temperature, momentum, num_data -- what a scheduler or a runner changes between steps)
+        into the device control block, so that the next replay of a captured step uses them.
+        Eager calls do this themselves; only graph replays need it."""
+        if not self.capturable:
+            return
+        for group, fg in zip(self.param_groups, self._flat):
+            for phase in (N.PHASE_INITIAL, N.PHASE_MID, N.PHASE_FINAL):
+                self._update_group_for(group, phase)
+                fg.poke_coef(phase, self._coefs(group, fg, phase))
+
     def _step_fn(self, group, fg: FlatGroup, chunks, calc_metrics=True, is_final=False):
         """One SGLD transition of a whole group (mcmc/sgld.py:119-154); a final step only produces
         the diagnostics and leaves parameters and momentum alone."""
@@ -220,27 +335,23 @@ class SGLD(torch.optim.Optimizer):
                                         "associated with a value")
             flags |= N.F_MM_PRE_NOISE
         if is_final:
-            if not (calc_metrics or self.raise_on_nan):
+            if not calc_metrics:
                 return
             noise = N.NOISE_NONE
-            # no writes; m' = 1*m so that the sums describe the stored momentum
-            fg.launch(self._OP, N.PHASE_FINAL, flags, noise, cm=1.0 if a > 0 else 0.0,
-                      inv_num_data=inv_n, chunks=chunks)
+            fg.launch_coef(self._OP, N.PHASE_FINAL, flags, noise, self._coefs(group, fg, N.PHASE_FINAL), chunks)
         else:
             flags |= N.F_WRITE_P | N.F_UPDATE_SQ
             if a > 0:
                 flags |= N.F_WRITE_M
             flags |= fg.step_prior_flags(pf, chunks)
             noise = fg.take_noise_mode(group['temperature'] > 0)
-            fg.launch(self._OP, N.PHASE_MID, flags, noise,
-                      cm=a, cg=-group['hn'], cn=group['noise_std'], cp=group['h'],
-                      inv_num_data=inv_n, rms_alpha=group['rmsprop_alpha'], chunks=chunks)
+            fg.launch_coef(self._OP, N.PHASE_MID, flags, noise, self._coefs(group, fg, N.PHASE_MID), chunks)
             if noise != N.NOISE_NONE:
                 self._consume_replay(fg)
         if calc_metrics:
             fg.have_metrics = True
             fg.metrics_num_data = group['num_data']
-        fg.note_step_sums(flags, self._OP)
+        fg.note_step_sums(flags, self._OP, capture_grads=False)     # SGLD has no point energy to keep fresh
         if flags & N.F_HYPER_POST:
             fg.after_hyper_post()
 

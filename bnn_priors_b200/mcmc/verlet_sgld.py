@@ -37,7 +37,7 @@ class VerletSGLD(SGLD):
         """Make SUM_GG (and SUM_MM) in the segment state describe the current
         p.grad / momentum: free right after a step, one read-only launch if
         somebody changed them since."""
-        fg.sync_views(raise_on_no_grad=True)     # a re-bound p.grad is copied in (and bumps the version)
+        fg.sync_views(raise_on_no_grad=True)     # the gradient pointers follow a re-bound p.grad
         if not fg.sums_fresh(need_mm=self._OP == N.OP_HMC):
             fg.reduce_now(1.0 / group['num_data'] if fg.prior_fused else 0.0)
 
@@ -111,6 +111,15 @@ class VerletSGLD(SGLD):
         g['mom_decay'], g['grad_v'], g['noise_std'] = self._phase_scalars(
             g['momentum'], g['temperature'], phase)
 
+    def _update_group_for(self, group, phase: int) -> None:
+        self._update_group_fn(group, phase=phase)
+
+    def _coefs(self, group, fg: FlatGroup, phase: int):
+        bhn = group['bhn']
+        inv_n = 1.0 / group['num_data'] if fg.prior_fused else 0.0
+        return (group['mom_decay'], -.5 * group['grad_v'] * bhn, group['noise_std'], group['bh'], inv_n,
+                -.5 * bhn, group['num_data']**2 * group['b^2h^2'] / 8, group['rmsprop_alpha'])
+
     def _transition(self, phase, closure, **step_kwargs):
         if phase != N.PHASE_MID:
             # keep a `torch.optim.lr_scheduler` happy (verlet_sgld.py:95,128)
@@ -119,19 +128,22 @@ class VerletSGLD(SGLD):
                                    is_initial=(phase == N.PHASE_INITIAL), is_final=(phase == N.PHASE_FINAL),
                                    **step_kwargs)
 
-    @torch.no_grad()
     def initial_step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
                      save_state=True, calc_metrics=True):
         "First transition after (re)sampling / accepting: optionally snapshots the state for a rejection."
         return self._transition(N.PHASE_INITIAL, closure, save_state=save_state, calc_metrics=calc_metrics)
 
-    @torch.no_grad()
+    def _step_impl(self, closure: Optional[Callable[..., torch.Tensor]] = None, calc_metrics=True):
+        return self._transition(N.PHASE_MID, closure, calc_metrics=calc_metrics)
+
     def step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
              calc_metrics=True):
         "An intermediate transition."
+        if self._hooks_active():
+            return self._hooked("step", closure, calc_metrics=calc_metrics)
         return self._transition(N.PHASE_MID, closure, calc_metrics=calc_metrics)
+    step.hooked = True
 
-    @torch.no_grad()
     def final_step(self, closure: Optional[Callable[..., torch.Tensor]] = None,
                    calc_metrics=True):
         "Last transition before the M-H test: completes the momentum, leaves the parameters where they are."
@@ -160,12 +172,8 @@ class VerletSGLD(SGLD):
         noise = fg.take_noise_mode(True)
         if noise == N.NOISE_PHILOX and group['noise_std'] == 0.0:
             noise = N.NOISE_NONE
-        bhn = group['bhn']
-        fg.launch(self._OP, self._phase(is_initial, is_final), flags, noise,
-                  cm=group['mom_decay'], cg=-.5 * group['grad_v'] * bhn, cn=group['noise_std'],
-                  cp=group['bh'], inv_num_data=inv_n, c_gm_base=-.5 * bhn,
-                  curv_base=group['num_data']**2 * group['b^2h^2'] / 8,
-                  rms_alpha=group['rmsprop_alpha'], chunks=chunks)
+        phase = self._phase(is_initial, is_final)
+        fg.launch_coef(self._OP, phase, flags, noise, self._coefs(group, fg, phase), chunks)
         self._consume_replay(fg)
         if calc_metrics:
             fg.have_metrics = True
@@ -173,6 +181,8 @@ class VerletSGLD(SGLD):
         fg.have_prev_new = True
         if is_initial:
             fg.have_delta = True
-        fg.note_step_sums(flags, self._OP)
+        # delta_energy() / _point_energy() follow initial / final steps and steps that log metrics
+        # (inference.py:321-358, inference_reject.py:96-123): remember which gradient SUM_GG describes
+        fg.note_step_sums(flags, self._OP, capture_grads=(is_initial or is_final or calc_metrics))
         if flags & N.F_HYPER_POST:
             fg.after_hyper_post()

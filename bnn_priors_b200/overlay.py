@@ -13,6 +13,10 @@ imported by name into inference.py:6 and inference_reject.py:6, reached as
 `exp_utils.evaluate_model` by experiments/train_bnn.py:148-149 and eval_bnn.py:62) to the
 device-side evaluation of `bnn_priors_b200.evaluate`.
 
+`install(sample_sink=True)` re-binds `exp_utils.HDF5ModelSaver` (the sample file writer train_bnn.py
+constructs, :201-203) to `sample_sink.FlatSampleSaver`: one device-to-device snapshot + one asynchronous
+device-to-host copy per sample instead of one blocking copy per tensor, same file.
+
 `install(fuse_prior=True)` also takes the prior out of autograd under an UNCHANGED runner:
 every runner class's `_make_optimizer` (inference.py:89,298,368; inference_reject.py:12,183,192)
 is wrapped so that the sampler it returns gets `fuse_prior(self.model, sampler,
@@ -114,7 +118,22 @@ def _install_fuse_prior(pkg: str) -> None:
                 cls._exact_model_potential_and_grad = wrap_exact(cls.__dict__["_exact_model_potential_and_grad"])
 
 
-def install(reference_package: str = "bnn_priors", evaluate: bool = False, fuse_prior: bool = False) -> None:
+def _install_sample_sink(pkg: str) -> None:
+    """exp_utils.HDF5ModelSaver (exp_utils.py:409-487; constructed by experiments/train_bnn.py:201-203 as
+    `exp_utils.HDF5ModelSaver(path, "w")`) -> sample_sink.FlatSampleSaver, same constructor arguments.
+    HDF5Metrics, a subclass defined in the same module, keeps the original base class."""
+    from .sample_sink import FlatSampleSaver
+    name = f"{pkg}.exp_utils"
+    try:
+        m = sys.modules.get(name) or importlib.import_module(name)
+    except ImportError:
+        return
+    _saved["model_saver"] = m.HDF5ModelSaver
+    m.HDF5ModelSaver = FlatSampleSaver
+
+
+def install(reference_package: str = "bnn_priors", evaluate: bool = False, fuse_prior: bool = False,
+            sample_sink: bool = False) -> None:
     from . import mcmc as fast
     ref = importlib.import_module(reference_package + ".mcmc")
     if "classes" not in _saved:
@@ -133,6 +152,8 @@ def install(reference_package: str = "bnn_priors", evaluate: bool = False, fuse_
         _install_evaluate(reference_package)
     if fuse_prior and "runner_methods" not in _saved:
         _install_fuse_prior(reference_package)
+    if sample_sink and "model_saver" not in _saved:
+        _install_sample_sink(reference_package)
 
 
 def uninstall() -> None:
@@ -146,6 +167,10 @@ def uninstall() -> None:
         m = sys.modules.get(f"{pkg}.mcmc.{sub}")
         for n, c in names.items():
             setattr(m, n, c)
+    if "model_saver" in _saved:
+        m = sys.modules.get(f"{pkg}.exp_utils")
+        if m is not None:
+            m.HDF5ModelSaver = _saved["model_saver"]
     for cls, name, fn in reversed(_saved.get("runner_methods", [])):
         setattr(cls, name, fn)
     for sub, fn in _saved.get("evaluate", {}).items():

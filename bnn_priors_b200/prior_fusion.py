@@ -344,7 +344,7 @@ class FusedPrior:
                     fg.hyper_prepass(inv_n)       # scales, log-prior and hyper gradients in one read of P
             elif not fg.log_prior_fresh():
                 fg.sync_views(raise_on_no_grad=False)
-                fg.reduce_now(inv_n)
+                fg.reduce_log_prior(inv_n)      # reads P only: legal while p.grad is None
             fg.flush_pending()          # the sum lives in the segment state once the last launch's epilogue ran
             v = fg.state_dev[:, N.S_LOG_PRIOR].sum()
             total = v if total is None else total + v

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BNNP_ABI_VERSION 8
+#define BNNP_ABI_VERSION 9
 
 #define BNNP_SEG_ALIGN 32      /* floats: every segment starts on a 128-byte line */
 #ifndef BNNP_THREADS
@@ -211,9 +211,37 @@ typedef struct BnnpEpilogue {
     double inv_num_data;     /* 1/N (BNNP_F_HYPER)                                   */
 } BnnpEpilogue;
 
+/* Coefficients of one kind of launch, as they sit in a device control block (BnnpControl). */
+typedef struct BnnpCoef {
+    double cm, cg, cn, cp;
+    double inv_num_data;
+    double c_gm_base, curv_base, rms_alpha;
+} BnnpCoef;
+
+#define BNNP_COEF_SLOTS 4      /* by convention: the sampler's PHASE_INITIAL / MID / FINAL transition
+                                  and sample_momentum                                  */
+
+/* Device-resident launch state of one chain ("capturable" mode).  A launch whose BnnpLaunch.ctl
+ * points here takes its Philox counter, its parity (and with it the walking direction,
+ * BNNP_F_REVERSE), the pending epilogue and its coefficients (slot BnnpLaunch.coef_slot) from
+ * this block instead of from the kernel parameters, and bnnp_advance -- enqueued right after it --
+ * moves the block on: pending <- this launch's epilogue, call += 1, parity ^= 1.  Nothing per-launch
+ * is baked into the kernel parameters any more, so a step can be captured in a CUDA graph and
+ * replayed: every replay draws new noise, alternates the direction and folds the previous replay's
+ * sums, and a learning-rate / temperature change between replays is a bnnp_poke of the coefficient
+ * slots (sgld.py:114-117, verlet_sgld.py:96-146 recomputed on the host as before).             */
+typedef struct BnnpControl {
+    uint64_t call;             /* Philox counter words 2,3 of the NEXT launch             */
+    int32_t parity;            /* half of partials / stamps the NEXT launch writes         */
+    int32_t reserved;
+    BnnpEpilogue pending;      /* epilogue of the LAST launch (valid = 0: none)            */
+    BnnpCoef coef[BNNP_COEF_SLOTS];
+} BnnpControl;
+
 typedef struct BnnpLaunch {
     float* P;                  /* flat [total]                                      */
-    float* G;
+    float* G;                  /* flat [total]: p.grad of every tensor, unless seg_grad
+                                  is given; always the target of bnnp_rollback        */
     float* M;
     float* prev_p;             /* flat [total] or null (BNNP_F_SAVE_STATE)          */
     float* prev_g;
@@ -225,6 +253,14 @@ typedef struct BnnpLaunch {
     const int32_t* chunk_ids;  /* null: process chunks 0..nchunks-1; else [nchunks]
                                   chunk indices, whole segments only (used to skip
                                   tensors without a gradient, sgld.py:96-101)       */
+    const float* const* seg_grad;  /* null, or device array [nseg]: the gradient of segment s is
+                                  the contiguous, 16-byte aligned fp32 array seg_grad[s]
+                                  (numel_s floats) instead of G + off_s -- the tensors
+                                  autograd hands over after zero_grad() are read in place,
+                                  no copy into G (sgld.py:94-105 reads p.grad likewise)  */
+    BnnpControl* ctl;          /* null, or the chain's device control block: call, parity,
+                                  BNNP_F_REVERSE, pending and the coefficients cm..rms_alpha
+                                  of this struct are ignored and read from *ctl           */
     double* seg_state;         /* [nseg][BNNP_STATE_STRIDE]                         */
     double* partials;          /* scratch [2][nchunks_total][BNNP_NRED]             */
     uint64_t* stamps;          /* [2][nchunks_total], zero-initialised once         */
@@ -235,6 +271,8 @@ typedef struct BnnpLaunch {
                                   must differ from pending.parity                   */
     int32_t op, phase, noise;
     uint32_t flags;
+    int32_t coef_slot;         /* which BnnpControl.coef entry this launch uses (ctl != null) */
+    int32_t reserved;
     uint32_t key0, key1;       /* Philox key                                        */
     uint64_t call;             /* Philox counter words 2,3: one value per launch    */
     /* m' from cm*m, (cg*M)*g, cn*eps ;  p' = p + (cp*M)*m'   (M = precond)         */
@@ -284,6 +322,22 @@ int bnnp_launch(const BnnpLaunch* args, void* stream);
  * a launch that skips segments.  Reads segs, seg_state, partials, stamps, nseg,
  * nchunks_total and pending; no-op if pending.valid == 0. */
 int bnnp_finalize(const BnnpLaunch* args, void* stream);
+
+/* Capturable mode: move the control block on after a bnnp_launch with args->ctl != null (same
+ * args): ctl->pending <- that launch's epilogue (op, phase, flags from args; parity, call and the
+ * epilogue coefficients from *ctl), ctl->call += 1, ctl->parity ^= 1.  One tiny launch. */
+int bnnp_advance(const BnnpLaunch* args, void* stream);
+
+/* Capturable mode: bnnp_finalize applies ctl->pending when args->ctl != null; this clears it
+ * afterwards (ctl->pending.valid = 0). */
+int bnnp_clear_pending(BnnpControl* ctl, void* stream);
+
+/* Stream-ordered write of a small HOST buffer into device memory, carried in the parameters of a
+ * tiny kernel (nbytes <= 3840, a multiple of 4; dst 4-byte aligned): no pinned staging buffer whose
+ * lifetime the caller would have to manage, legal during stream capture.  Used for the per-segment
+ * gradient pointers (BnnpLaunch.seg_grad) when autograd moved a gradient, and for BnnpControl
+ * (initial state, coefficient slots). */
+int bnnp_poke(void* dst, const void* src_host, int64_t nbytes, void* stream);
 
 /* VerletSGLD.maybe_reject's restore (mcmc/verlet_sgld.py:63-69):
  * P,G,M <- prev_*  over `total` floats (prev_m/M may be null: momentum == 0). */

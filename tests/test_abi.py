@@ -123,10 +123,21 @@ def test_struct_layouts_match_header():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?[A-Za-z_0-9]+\s*\**", "", decl, count=1)
-        names += [x.strip().lstrip("*").strip() for x in decl.split(",")]
+        names += [re.search(r"([A-Za-z_0-9]+)\s*$", x).group(1) for x in decl.split(",")]     # the declarator's name
     assert names == [f[0] for f in N.BnnpLaunch._fields_]
     assert C.sizeof(N.BnnpLaunch) % 8 == 0
+    # the block the host writes with one struct.pack_into (nchunks .. pending) is contiguous and unpadded
+    assert N.DYN_OFFSET == N.BnnpLaunch.nchunks.offset and N.DYN_OFFSET + N.DYN_STRUCT.size == C.sizeof(N.BnnpLaunch)
+    for name, cls in (("BnnpCoef", N.BnnpCoef), ("BnnpControl", N.BnnpControl)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), HEADER, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        got = []
+        for decl in body.split(";"):
+            if decl.strip():
+                got += [re.search(r"([A-Za-z_0-9]+)\s*(\[[A-Z_]+\])?\s*$", x).group(1) for x in decl.split(",")]
+        assert got == [f[0] for f in cls._fields_], name
+    assert C.sizeof(N.BnnpCoef) == 64 and C.sizeof(N.BnnpControl) == 16 + 64 + 4 * 64
+    assert int(re.search(r"#define BNNP_COEF_SLOTS (\d+)", HEADER).group(1)) == N.COEF_SLOTS
 
 
 def test_plan_layout(lib):
@@ -185,6 +196,17 @@ def test_launch_validates_arguments_without_a_gpu(lib):
     a.flags, a.noise = N.F_READ_P, N.NOISE_REPLAY
     assert lib.bnnp_launch(C.byref(a), None) == -1 and b"replay" in lib.bnnp_last_error()
     assert lib.bnnp_rollback(None, None, None, None, None, None, 0, None) == -1
+    # capturable mode: control block entry points
+    b = N.BnnpLaunch()
+    assert lib.bnnp_advance(C.byref(b), None) == -1 and b"no control block" in lib.bnnp_last_error()
+    b.ctl, b.coef_slot = 4096, N.COEF_SLOTS
+    assert lib.bnnp_advance(C.byref(b), None) == -1 and b"coef_slot" in lib.bnnp_last_error()
+    assert lib.bnnp_clear_pending(None, None) == -1
+    buf = (C.c_char * 8)()
+    assert lib.bnnp_poke(None, buf, 8, None) == -1
+    assert lib.bnnp_poke(4096, buf, 6, None) == -1 and b"multiple of 4" in lib.bnnp_last_error()
+    assert lib.bnnp_poke(4096, buf, 4000, None) == -1
+    assert lib.bnnp_poke(4098, buf, 8, None) == -1
 
 
 def test_philox_key_matches_the_oracle_specification():

@@ -22,10 +22,21 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "param-updates/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("SGLD param-updates/sec") and d["config"]["workload"] and d["config"]["n_params"] == 25124842
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert set(d["cpu_arms"]) == {"numpy_port_one_subchain_per_thread", "torch_ops_like_the_reference"}
+    assert set(d["cpu_arms"]) >= {"numpy_port_one_subchain_per_thread", "torch_ops_like_the_reference"}
     assert d["value"] == max(a["value"] for a in d["cpu_arms"].values())
+    assert d["steps"] == 1 and d["warmup"] == 1 or d["cpu_baseline"]["kind"] == "reference"
+    # both arms of the bench describe the workload with the same keys (the driver compares them)
+    assert set(d["config"]) == {"workload", "n_params", "tensors", "sampler", "calc_metrics", "lr", "num_data",
+                                "momentum", "temperature", "chains", "parallelism", "l2"}
+    assert d["config"]["tensors"] == 54
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bnn_priors", "mcmc", "sgld.py")):
+        # the unmodified reference classes were timed too
+        assert d["cpu_arms"]["reference_bnn_priors_mcmc_SGLD"]["kind"] == "reference"
+        assert {"SGLD.step(calc_metrics=False)", "VerletSGLD.step(calc_metrics=True)", "HMC.step(calc_metrics=False)",
+                "VerletSGLD.delta_energy", "VerletSGLD.maybe_reject(rejecting)"} <= set(d["reference_calls"])
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():

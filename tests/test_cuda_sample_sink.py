@@ -27,9 +27,11 @@ def test_sink_stores_what_the_reference_saver_would(tmp_path):
             opt.step(calc_metrics=False)
 
     opt.sample_momentum()
-    path = tmp_path / "samples.pt"
+    path = tmp_path / "samples.pth"       # .pth: the torch.save format even where an h5py is importable
     want = []
-    with FlatSampleSaver(str(path), opt, capacity=5) as saver:
+    # constructed like the reference's saver, BEFORE it knows any sampler (train_bnn.py:201-203); two
+    # staging slots for four samples: the sink drains to the file as it goes
+    with FlatSampleSaver(str(path), "w", slots=2) as saver:
         for s in range(4):
             move(3)
             sd = model.state_dict()
@@ -37,6 +39,13 @@ def test_sink_stores_what_the_reference_saver_would(tmp_path):
             saver.add_state_dict(sd, step=100 + 7 * s)
             saver.flush()
             move(1)                       # the chain moves on at once; the stored sample must not
+            if s == 2:
+                # a killed run keeps what was flushed: the first samples are already in the file
+                from bnn_priors_b200.sample_sink import recover_rows
+                torch.cuda.synchronize()
+                saver.flush()
+                assert recover_rows(str(path))["steps"].tolist() == [100, 107, 114]
+        assert saver.sampler is opt           # found through the parameters it owns
         in_ram = saver.load_samples(keep_steps=False)
     on_disk = torch.load(str(path))       # exp_utils.load_samples' fallback for non-HDF5 files
     keys = list(want[0].keys())
@@ -57,16 +66,59 @@ def test_sink_stores_what_the_reference_saver_would(tmp_path):
     assert on_disk[nb].tolist() == [3, 7, 11, 15]
 
 
-def test_sink_capacity_and_ram_only():
+def test_sink_grows_and_ram_only():
     from bnn_priors_b200 import mcmc
     from bnn_priors_b200.sample_sink import FlatSampleSaver
     lin = torch.nn.Linear(8, 4).to(DEV)
     opt = mcmc.SGLD(list(lin.parameters()), lr=1e-2, num_data=1.0)
-    saver = FlatSampleSaver(None, opt, capacity=1)
+    saver = FlatSampleSaver(None, opt, capacity=1)       # round-1 signature still accepted; capacity is ignored
     assert saver.load_samples() == {}
-    saver.add_state_dict(lin.state_dict(), 0)
-    with pytest.raises(IndexError):
-        saver.add_state_dict(lin.state_dict(), 1)
+    want = []
+    for i in range(7):                                   # more samples than staging slots
+        with torch.no_grad():
+            lin.weight.add_(1.0)
+        want.append(lin.weight.detach().cpu().clone())
+        saver.add_state_dict(lin.state_dict(), i)
     saver.flush(final=True)
     out = saver.load_samples()
-    assert torch.equal(out["weight"][0], lin.weight.detach().cpu()) and out["steps"].tolist() == [0]
+    assert torch.equal(out["weight"], torch.stack(want)) and out["steps"].tolist() == list(range(7))
+    saver.close()
+    with pytest.raises(RuntimeError):
+        saver.add_state_dict(lin.state_dict(), 8)
+
+
+def test_sink_writes_the_reference_hdf5_layout_incrementally_and_the_reference_reads_it(tmp_path):
+    """With h5py importable (here: the test stand-in with h5py's API, tests/golden/_shims/h5py) the sink
+    grows the reference's HDF5 file row by row and the REFERENCE's own load_samples
+    (exp_utils.py:539-551, from oracle/_ref) reads it back."""
+    import refenv
+    if not refenv.available():
+        pytest.skip("no oracle/_ref snapshot")
+    eu = refenv.exp_utils()
+    from bnn_priors_b200 import mcmc
+    from bnn_priors_b200.sample_sink import FlatSampleSaver
+    torch.manual_seed(1)
+    model = LM.TinyClassifier(20, 4, 16, extra_bn=True).to(DEV)
+    opt = mcmc.SGLD(list(model.parameters()), lr=1e-2, num_data=96.0, momentum=0.9)
+    path = str(tmp_path / "samples.h5")
+    want = []
+    with FlatSampleSaver(path, "w") as saver:
+        for s in range(3):
+            with torch.no_grad():
+                for p in model.parameters():
+                    p.add_(0.5)
+            sd = model.state_dict()
+            want.append({k: v.cpu().detach().clone() for k, v in sd.items()})
+            saver.add_state_dict(sd, step=10 * s)
+            torch.cuda.synchronize()
+            saver.flush()
+            partial = eu.load_samples(path)              # readable while the run goes on
+            assert partial["steps"].tolist() == [10 * i for i in range(s + 1)]
+    got = eu.load_samples(path, keep_steps=False)
+    assert list(got.keys()) == list(want[0].keys())
+    for k in got:
+        assert torch.equal(got[k], torch.stack([w[k] for w in want])), k
+    import h5py
+    with h5py.File(path, "r") as f:
+        d = f[list(want[0].keys())[0]]
+        assert d.chunks == (1,) + tuple(d.shape[1:]) and d.maxshape[0] is None and d.fletcher32

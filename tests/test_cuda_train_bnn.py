@@ -39,10 +39,13 @@ def _spy(monkeypatch):
 ])
 @pytest.mark.parametrize("fuse", [False, True])
 def test_train_bnn_main_with_the_overlay(tmp_path, monkeypatch, inference, model, data, prior, extra, fuse):
+    """fuse=False: samplers + evaluation re-bound; fuse=True: everything the overlay offers -- the prior fused
+    into the kernel and the sample file written by FlatSampleSaver (in the reference's HDF5 layout, through
+    the h5py stand-in) and read back by the reference's own load_samples inside main."""
     import runner_harness as H
     from bnn_priors_b200 import mcmc as fast, overlay
     made = _spy(monkeypatch)
-    overlay.install(evaluate=True, fuse_prior=fuse)
+    overlay.install(evaluate=True, fuse_prior=fuse, sample_sink=fuse)
     try:
         run, rundir = H.run_train_bnn(tmp_path, inference=inference, model=model, data=data, weight_prior=prior,
                                       n_train=512, n_test=256, **extra)
