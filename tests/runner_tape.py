@@ -201,8 +201,8 @@ def replaying_class(base, tape: Tape, report: Report, fused_prior: bool = False)
                 assert abs(have - want) <= 1e-12 * max(1.0, abs(want)), f"{op}: group[{k}] {have} != {want}"
             report.n_events += 1
             report.ops[op] = report.ops.get(op, 0) + 1
-            if "pg_abs" in ev:
-                self._last_pg_abs = ev["pg_abs"]
+            if "pg_abs" in ev and ev["kwargs"].get("calc_metrics", True):
+                self._last_pg_abs = ev["pg_abs"]     # the step that (re)computes est_config_temp
             if op in STEP_OPS:
                 for i, (p, g) in enumerate(zip(params, ev["grads"])):
                     if g is None:
