@@ -681,6 +681,10 @@ class FlatGroup:
         "capturable mode: coefficient slot `slot` of the device control block <- coef (if it differs)"
         if self._slot_cache[slot] == tuple(coef):
             return
+        if slot != N.SLOT_OTHER and torch.cuda.is_current_stream_capturing():
+            # a write recorded in a graph would be repeated by every replay and undo later updates
+            raise RuntimeError("the sampler's hyper-parameters (lr / temperature / momentum / num_data) changed since "
+                               "its last launch: call `sync_hyperparameters()` before capturing a CUDA graph")
         raw = N.COEF_STRUCT.pack(*coef)
         dst = self.ctl_dev.data_ptr() + N.BnnpControl.coef.offset + slot * N.COEF_STRUCT.size
         with torch.cuda.device(self.device):

@@ -150,17 +150,21 @@ class SGLD(torch.optim.Optimizer):
         return fn(self, *args, **kwargs)
 
     def state_dict(self):
-        """torch's state_dict plus `square_avg` (the engine keeps only its mean; written out as the
+        """torch's state_dict with every per-parameter state as a PLAIN dict (a snapshot of the lazy,
+        device-backed one) plus `square_avg` (the engine keeps only its mean; written out as the
         constant tensor with that mean, which is all `update_preconditioner` reads: sgld.py:170-173)."""
-        for fg in self._flat:
-            for i, s in enumerate(fg.seg_states):
-                s.raw_set('square_avg', fg.square_avg_tensor(i))
-        try:
-            return super().state_dict()
-        finally:
-            for fg in self._flat:
-                for s in fg.seg_states:
-                    dict.pop(s, 'square_avg', None)
+        from ._flat import SegState
+        sd = super().state_dict()
+        plain = {}
+        for idx, st in sd['state'].items():
+            if isinstance(st, SegState):
+                d = dict(st.items())
+                d['square_avg'] = st._fg.square_avg_tensor(st._i)
+                plain[idx] = d
+            else:
+                plain[idx] = st
+        sd['state'] = plain
+        return sd
 
     def load_state_dict(self, state_dict):
         """torch replaces `self.state[p]` by plain dicts; route the loaded values back into the flat
@@ -267,7 +271,7 @@ class SGLD(torch.optim.Optimizer):
         launch over the gradients (4 B/param) + the read-back of the per-tensor flags; only with
         `raise_on_nan=True` (HMC's default)."""
         fg.launch(N.OP_REDUCE, N.PHASE_MID, N.F_READ_G, N.NOISE_NONE, cm=1.0, chunks=chunks)
-        fg.invalidate_sums()
+        fg._gg_sig = None
         st = fg.fetch()
         for i, p in enumerate(fg.params):
             if i not in missing and st[i, N.S_NONFINITE] != 0.0:

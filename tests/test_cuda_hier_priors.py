@@ -130,6 +130,10 @@ def test_fused_hierarchical_prior_follows_autograd(base, hyper, extra, sampler):
             opt.zero_grad()
             loss, log_prior, potential = model.split_potential_and_acc(x, y, 64.0)
             potential.backward()
+            # the rest of the reference runner's _model_potential_and_grad (inference.py:219-220): every
+            # parameter must HAVE a gradient here, also a fused hyper-parameter that autograd no longer reaches
+            for p in opt.param_groups[0]["params"]:
+                p.grad.clamp_(min=-1e6, max=1e6)
             vals.append((float(loss), float(log_prior)))
         assert vals[0][0] == pytest.approx(vals[1][0], rel=2e-5, abs=1e-6)
         assert vals[0][1] == pytest.approx(vals[1][1], rel=5e-6, abs=1e-4), (it, vals)

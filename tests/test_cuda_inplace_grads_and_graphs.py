@@ -71,9 +71,9 @@ def test_foreign_gradients_are_read_in_place_and_give_the_same_bits(kind):
         assert torch.equal(x, y)
     (fg,) = b.flat_groups
     assert fg.copies == 0                      # nothing was copied into G
-    for p in pb:
+    for p, q in zip(pa, pb):
         for k in ("est_temperature", "est_config_temp"):
-            assert b.state[p][k] == a.state[pa[pb.index(p)]][k]
+            assert a.state[p][k] == b.state[q][k]
     if kind != "SGLD":
         assert a.delta_energy(1.0, 1.5) == b.delta_energy(1.0, 1.5)
 
@@ -225,9 +225,9 @@ def test_a_captured_forward_backward_step_iteration_replays_to_the_eager_bits(ki
     graph = torch.cuda.CUDAGraph()
     opt.param_groups[0]["lr"] = lrs[n_warm]
     opt.sync_hyperparameters()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph):              # recording only: nothing runs yet
         static_loss = iteration(net, opt)
-    for lr in lrs[n_warm + 1:]:
+    for lr in lrs[n_warm:]:
         opt.param_groups[0]["lr"] = lr
         opt.sync_hyperparameters()             # a changed lr reaches the graph through the control block
         graph.replay()
@@ -239,6 +239,27 @@ def test_a_captured_forward_backward_step_iteration_replays_to_the_eager_bits(ki
     assert torch.isfinite(static_loss)
     if kind == "VerletSGLD":
         assert opts[0].delta_energy(0.0, 0.1) == opts[1].delta_energy(0.0, 0.1)
+
+
+def test_a_stale_coefficient_is_not_baked_into_a_graph():
+    opt, params = _make("SGLD", capturable=True)
+    opt.sample_momentum()
+    for p in params:
+        p.grad = torch.randn_like(p)
+    opt.step(calc_metrics=False)
+    opt.param_groups[0]["lr"] = 1e-4            # changed behind the sampler's back, no eager step since
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="sync_hyperparameters"):
+        with torch.cuda.graph(torch.cuda.CUDAGraph()):
+            opt.step(calc_metrics=False)
+    torch.cuda.synchronize()
+    opt.sync_hyperparameters()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        opt.step(calc_metrics=False)
+    g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(p).all() for p in params)
 
 
 def test_state_dict_round_trip():

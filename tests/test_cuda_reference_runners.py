@@ -53,15 +53,15 @@ def _check(report, tape, runner_a, runner_b, name):
             assert report.scalar_err[k] <= TOL, (k, d)
     assert report.de_term_err <= TOL, d
     assert report.decisions_equal == report.decisions, d
-    # what the runner stored as samples (inference.py:189-194)
+    # what the runner stored as samples (inference.py:189-194): the parameters.  (The BatchNorm running
+    # statistics in the same state_dict follow the minibatch order, which the Reject runners draw from OS
+    # entropy, inference_reject.py:68-72: not a function of the sampler.)
     sa, sb = runner_a.get_samples(), runner_b.get_samples()
     assert sa.keys() == sb.keys()
     import runner_tape as RT
-    for k in sa:
-        if sa[k].dtype.is_floating_point and sa[k].numel():
-            assert RT.rel_err(sb[k], sa[k]) <= TOL, k
-        else:
-            assert torch.equal(sa[k], sb[k]), k
+    for k in runner_a.param_names:
+        assert sa[k].shape == sb[k].shape and sa[k].shape[0] >= 2, k
+        assert RT.rel_err(sb[k], sa[k]) <= TOL, k
 
 
 def _run_case(name, fused=False, before_run=None):

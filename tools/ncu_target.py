@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""A short, fixed sequence of launches of one step-kernel variant for ncu (GPU box only).
+
+    ncu ... python tools/ncu_target.py <case> [n]
+
+cases: sgld | sgld_metrics | verlet | verlet_fused | verlet_save | hmc | sgld_foreign (the gradient read in
+place from tensors of their own, as after the runner's zero_grad() + backward())."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+case = sys.argv[1] if len(sys.argv) > 1 else "sgld"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+dev = torch.device("cuda", 0)
+smp, fused, call = {
+    "sgld": ("SGLD", False, lambda o: o.step(calc_metrics=False)),
+    "sgld_foreign": ("SGLD", False, lambda o: o.step(calc_metrics=False)),
+    "sgld_metrics": ("SGLD", False, lambda o: o.step(calc_metrics=True)),
+    "verlet": ("VerletSGLD", False, lambda o: o.step(calc_metrics=False)),
+    "verlet_fused": ("VerletSGLD", True, lambda o: o.step(calc_metrics=False)),
+    "verlet_save": ("VerletSGLD", False, lambda o: o.initial_step(save_state=True, calc_metrics=False)),
+    "hmc": ("HMC", False, lambda o: o.step(calc_metrics=False)),
+}[case]
+opt, params, fg = bench.make_chain(dev, 0, smp, fused_prior=fused)
+if case == "sgld_foreign":
+    bufs = [torch.randn_like(p) * 1e-3 for p in params]
+    for _ in range(n):
+        opt.zero_grad()
+        for p, g in zip(params, bufs):
+            p.grad = g.view_as(g)
+        call(opt)
+    assert fg.copies == 0
+else:
+    call(opt)
+    for _ in range(n - 1):
+        fg.relaunch()
+torch.cuda.synchronize()
+print(case, "launches", fg.launches)
