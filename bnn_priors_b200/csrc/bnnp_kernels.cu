@@ -111,11 +111,26 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
+#ifndef BNNP_LEAN_BM
+#define BNNP_LEAN_BM 1
+#endif
+__device__ __forceinline__ float fast_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float& z0, float& z1) {
     const float u = fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0, 1]
     const float t = fmaf(__uint2float_rn(y), 2.3283064365386963e-10f, -0.5f);                     // [-.5, .5]
     const float theta = t * 6.283185307179586f;
+    // sqrt(-2 ln u) = sqrt(-2 ln2 * log2 u); u >= 2^-33 is a normal number, so the bare MUFU.LG2 is enough
+    // (what __logf does as well, minus its denormal / special-case handling)
+#if BNNP_LEAN_BM
+    const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u));
+#else
     const float r = fast_sqrt(-2.0f * __logf(u));
+#endif
     float s, c;
     __sincosf(theta, &s, &c);
     z0 = r * c;
@@ -424,7 +439,7 @@ enum { SUMS_MIN = 0,      // g.g and the non-finite probe
 
 // One float4 of every stream.  Lanes >= `valid` (only the quad that straddles the end
 // of a segment has valid < 4) arrive zeroed and stay zero.
-template <int NOISE, bool PRIOR, int KIND, bool NOISE_FIRST, int SUMS>
+template <int NOISE, bool PRIOR, int KIND, bool NOISE_FIRST, int SUMS, bool FULL>
 __device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c, const PriorConst& pc, int valid,
                                             F4& p, const F4& g, F4& m, const float eps[4], float acc[BNNP_NRED]) {
 #pragma unroll
@@ -433,7 +448,7 @@ __device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c,
         float gj = g.f[j];
         acc[R_NONFINITE] = fmaf(gj, 0.0f, acc[R_NONFINITE]);   // 0, or NaN once g is inf/NaN
         if (PRIOR) {
-            if (KIND != F_NONE && (flags & BNNP_F_PRIOR_GRAD) && j < valid) gj += prior_grad_term<KIND>(pc, p0);
+            if (KIND != F_NONE && (flags & BNNP_F_PRIOR_GRAD) && (FULL || j < valid)) gj += prior_grad_term<KIND>(pc, p0);
             if (flags & BNNP_F_CLAMP_GRAD) gj = fminf(fmaxf(gj, -c.gmax), c.gmax);
         }
         float t, pre;
@@ -461,7 +476,7 @@ __device__ __forceinline__ void update_quad(const uint32_t flags, const Coef& c,
         }
         const float pn = fmaf(c.cpM, t, p0);      // stored only with BNNP_F_WRITE_P
         if (PRIOR && KIND != F_NONE && KIND != F_CONST) {
-            if ((flags & BNNP_F_LOG_PRIOR) && j < valid)
+            if ((flags & BNNP_F_LOG_PRIOR) && (FULL || j < valid))
                 acc[R_LOGP] += log_prior_term<KIND>(pc, (flags & BNNP_F_WRITE_P) ? pn : p0);
         }
         p.f[j] = pn;
@@ -671,7 +686,7 @@ struct ChunkCtx {
 
 // Noise + update + stores for the UNROLL quads of one thread; the prior kind is a
 // template parameter so the per-segment switch happens once per CTA.
-template <int NOISE, bool PRIOR, int KIND, bool NOISE_FIRST, int SUMS>
+template <int NOISE, bool PRIOR, int KIND, bool NOISE_FIRST, int SUMS, bool FULL>
 __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCtx& cx, const Coef& c,
                                               const PriorConst& pc, const PhiloxKeys& keys, F4 (&p)[UNROLL],
                                               F4 (&g)[UNROLL], F4 (&m)[UNROLL], F4 (&z)[UNROLL],
@@ -679,7 +694,7 @@ __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCt
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const int e = (u * THREADS + cx.tid) * 4;
-        if (e >= cx.rem) continue;
+        if (!FULL && e >= cx.rem) continue;
         const int64_t fi = cx.fbase + e;
         if (flags & BNNP_F_SAVE_STATE) {   // verlet_sgld.py:72-83, the values BEFORE the update
             st_f4_hint(L.prev_p + fi, p[u].v, POLICY_EVICT_FIRST);
@@ -687,13 +702,13 @@ __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCt
             if (L.prev_m != nullptr) st_f4_hint(L.prev_m + fi, m[u].v, POLICY_EVICT_FIRST);
         }
         if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)fi >> 2, call, keys, z[u].f);
-        const int valid = cx.rem - e;
-        if (valid < 4) {   // the quad that straddles the segment end: padding lanes are zeros
+        const int valid = FULL ? 4 : cx.rem - e;
+        if (!FULL && valid < 4) {   // the quad that straddles the segment end: padding lanes are zeros
 #pragma unroll
             for (int j = 1; j < 4; ++j)
                 if (j >= valid) p[u].f[j] = g[u].f[j] = m[u].f[j] = z[u].f[j] = 0.0f;
         }
-        update_quad<NOISE, PRIOR, KIND, NOISE_FIRST, SUMS>(flags, c, pc, valid, p[u], g[u], m[u], z[u].f, acc);
+        update_quad<NOISE, PRIOR, KIND, NOISE_FIRST, SUMS, FULL>(flags, c, pc, valid, p[u], g[u], m[u], z[u].f, acc);
         if (flags & BNNP_F_WRITE_P) st_state(L.P + fi, p[u].v);
         if (flags & BNNP_F_WRITE_M) st_state(L.M + fi, m[u].v);
     }
@@ -712,6 +727,69 @@ template <int NOISE, int SUMS, bool PRIOR>
 constexpr int min_ctas() {
     return (NOISE != BNNP_NOISE_REPLAY && SUMS != 2) ? (PRIOR ? BNNP_PRIOR_MIN_CTAS : BNNP_MIN_CTAS)
                                                      : (BNNP_MIN_CTAS > 3 ? 3 : BNNP_MIN_CTAS);
+}
+
+#ifndef BNNP_FULL_MODE
+#define BNNP_FULL_MODE 2    // 0: general path only; 1: full-chunk fast path everywhere; 2: for SUMS_ALL variants
+#endif
+// Loads, noise, prior, update and stores of one chunk; the partial sums come back in `acc`.
+template <int NOISE, bool PRIOR, bool NOISE_FIRST, int SUMS, bool FULL>
+__device__ __forceinline__ void chunk_body(const BnnpLaunch& L, const PhiloxKeys& keys, const Dyn& dyn, const ChunkCtx& cx,
+                                           const Coef& c, const BnnpSegment& sd, int seg, const float* gsrc,
+                                           float acc[BNNP_NRED]) {
+    const uint32_t flags = dyn.flags;
+    const int tid = cx.tid;
+    // ---- front-batched 128-bit loads: 3 (4 with replay noise) x UNROLL in flight per thread
+    F4 p[UNROLL], g[UNROLL], m[UNROLL], z[UNROLL];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int e = (u * THREADS + tid) * 4;
+        if (FULL) {
+            p[u].v = ld_state(L.P + cx.fbase + e);
+            g[u].v = ld_grad(gsrc + e);
+            m[u].v = ld_state(L.M + cx.fbase + e);
+            if (NOISE == BNNP_NOISE_REPLAY) z[u].v = ld_f4(L.replay_noise + cx.fbase + e);
+            else z[u].v = zero4;
+        } else {
+            const bool act = e < cx.rem;
+            p[u].v = (act && (flags & BNNP_F_READ_P)) ? ld_state(L.P + cx.fbase + e) : zero4;
+            g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_grad(gsrc + e) : zero4;
+            m[u].v = (act && (flags & BNNP_F_READ_M)) ? ld_state(L.M + cx.fbase + e) : zero4;
+            if (NOISE == BNNP_NOISE_REPLAY) z[u].v = act ? ld_f4(L.replay_noise + cx.fbase + e) : zero4;
+            else z[u].v = zero4;
+        }
+    }
+
+    if (PRIOR) {
+        float hyper_term = 0.0f;
+        if (is_hyper_kind(sd.prior_kind)) {
+            // -(1/N) d log p / du, left by the epilogue of the BNNP_F_HYPER pre-pass (finalised before
+            // this launch started: bnnp_launch refuses a pending BNNP_F_HYPER epilogue)
+            hyper_term = (float)L.seg_state[(int64_t)seg * BNNP_STATE_STRIDE + BNNP_S_HYPER];
+        }
+#define BNNP_FORM_CASE(F)                                                                                      \
+    case F:                                                                                                    \
+        process_chunk<NOISE, true, F, NOISE_FIRST, SUMS, FULL>(L, cx, c, make_prior<F>(sd, dyn.inv_n, hyper_term), \
+                                                               keys, p, g, m, z, acc, flags, dyn.call);        \
+        break;
+        switch (prior_form(sd.prior_kind)) {   // uniform over the CTA: one closed form per segment
+            BNNP_FORM_CASE(F_NORMAL)
+#ifndef BNNP_ONLY_NORMAL
+            BNNP_FORM_CASE(F_LOGNORMAL)
+            BNNP_FORM_CASE(F_LAPLACE)
+            BNNP_FORM_CASE(F_STUDENT_T)
+            BNNP_FORM_CASE(F_GENNORM)
+            BNNP_FORM_CASE(F_DOUBLE_GAMMA)
+#endif
+            BNNP_FORM_CASE(F_CONST)
+            BNNP_FORM_CASE(F_NONE)
+        }
+#undef BNNP_FORM_CASE
+    } else {
+        process_chunk<NOISE, false, F_NONE, NOISE_FIRST, SUMS, FULL>(L, cx, c, PriorConst(), keys, p, g, m, z, acc, flags,
+                                                                     dyn.call);
+    }
 }
 
 template <int NOISE, bool PRIOR, bool NOISE_FIRST, int SUMS>
@@ -748,52 +826,20 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     c.cpM = (float)(dyn.cp * sd.precond);
     c.gmax = S.gmax;
 
-    // ---- front-batched 128-bit loads: 3 (4 with replay noise) x UNROLL in flight per thread
-    F4 p[UNROLL], g[UNROLL], m[UNROLL], z[UNROLL];
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-        const int e = (u * THREADS + tid) * 4;
-        const bool act = e < cx.rem;
-        p[u].v = (act && (flags & BNNP_F_READ_P)) ? ld_state(L.P + cx.fbase + e) : zero4;
-        g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_grad(gsrc + e) : zero4;
-        m[u].v = (act && (flags & BNNP_F_READ_M)) ? ld_state(L.M + cx.fbase + e) : zero4;
-        if (NOISE == BNNP_NOISE_REPLAY) z[u].v = act ? ld_f4(L.replay_noise + cx.fbase + e) : zero4;
-        else z[u].v = zero4;
-    }
-
     float acc[BNNP_NRED];
 #pragma unroll
     for (int k = 0; k < BNNP_NRED; ++k) acc[k] = 0.0f;
 
-    if (PRIOR) {
-        float hyper_term = 0.0f;
-        if (is_hyper_kind(sd.prior_kind)) {
-            // -(1/N) d log p / du, left by the epilogue of the BNNP_F_HYPER pre-pass (finalised before
-            // this launch started: bnnp_launch refuses a pending BNNP_F_HYPER epilogue)
-            hyper_term = (float)L.seg_state[(int64_t)seg * BNNP_STATE_STRIDE + BNNP_S_HYPER];
-        }
-#define BNNP_FORM_CASE(F)                                                                                      \
-    case F:                                                                                                    \
-        process_chunk<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, dyn.inv_n, hyper_term),    \
-                                                         keys, p, g, m, z, acc, flags, dyn.call);              \
-        break;
-        switch (prior_form(sd.prior_kind)) {   // uniform over the CTA: one closed form per segment
-            BNNP_FORM_CASE(F_NORMAL)
-#ifndef BNNP_ONLY_NORMAL
-            BNNP_FORM_CASE(F_LOGNORMAL)
-            BNNP_FORM_CASE(F_LAPLACE)
-            BNNP_FORM_CASE(F_STUDENT_T)
-            BNNP_FORM_CASE(F_GENNORM)
-            BNNP_FORM_CASE(F_DOUBLE_GAMMA)
-#endif
-            BNNP_FORM_CASE(F_CONST)
-            BNNP_FORM_CASE(F_NONE)
-        }
-#undef BNNP_FORM_CASE
-    } else {
-        process_chunk<NOISE, false, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, PriorConst(), keys, p, g, m, z, acc, flags, dyn.call);
-    }
+    // Nearly every chunk is a full one of a launch that reads all three streams: that case runs without
+    // the per-quad bounds / flag tests and without the zero fill (FULL), the rest (the last chunk of a
+    // tensor, launches that skip a stream) takes the general path.
+    constexpr uint32_t READ_ALL = BNNP_F_READ_P | BNNP_F_READ_G | BNNP_F_READ_M;
+    // (measured per variant, profiles/r02_notes.md: the split pays for the variants that reduce every sum)
+    constexpr bool SPLIT = BNNP_FULL_MODE == 1 || (BNNP_FULL_MODE == 2 && SUMS == SUMS_ALL);
+    if (SPLIT && cx.rem == CHUNK && (flags & READ_ALL) == READ_ALL)
+        chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, true>(L, keys, dyn, cx, c, sd, seg, gsrc, acc);
+    else
+        chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, false>(L, keys, dyn, cx, c, sd, seg, gsrc, acc);
 
     // ---- chunk reduction: fp32 butterfly inside the warp, fp64 across warps (fixed order)
     constexpr unsigned LIVE = (SUMS == SUMS_ALL) ? 0xffu

@@ -47,10 +47,17 @@ def _check(report, tape, runner_a, runner_b, name):
     assert report.n_events == len(tape.events)
     assert report.p_err <= TOL, d
     assert report.m_err <= TOL, d
-    for k in ("preconditioner", "est_temperature", "est_config_temp", "square_avg_mean", "delta_energy",
-              "prev_new_momentum_delta"):
+    for k in ("preconditioner", "est_temperature", "est_config_temp", "square_avg_mean"):
         if k in report.scalar_err:
             assert report.scalar_err[k] <= TOL, (k, d)
+    # the per-tensor running sums of the energy bookkeeping (verlet_sgld.py:170-176) add one signed
+    # c * dot(g, m) term per step, each rounded in fp32 by the reference's `dot` (fp64 here), and are
+    # judged against the largest of them at the event, not against the (unknown) sum of the magnitudes
+    # of everything that went in: a few 1e-6 per step.  The quantity they exist for, the total delta
+    # energy, is held to 1e-5 of the size of its terms just below.
+    for k in ("delta_energy", "prev_new_momentum_delta"):
+        if k in report.scalar_err:
+            assert report.scalar_err[k] <= 5 * TOL, (k, d)
     assert report.de_term_err <= TOL, d
     assert report.decisions_equal == report.decisions, d
     # what the runner stored as samples (inference.py:189-194): the parameters.  (The BatchNorm running
