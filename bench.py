@@ -360,15 +360,23 @@ def make_chain(device, seed, sampler="SGLD", tag=WORKLOAD, fused_prior=False, **
     return opt, params, fg
 
 
+LEAD_IN = 2      # untimed calls between the barrier and the first timed one (see timed_gpu)
+
+
 def timed_gpu(fn, steps, device, dist_on):
-    """K calls of fn bracketed by barrier + synchronize, CUDA events on the current
-    stream; returns milliseconds (max over ranks)."""
+    """K calls of fn bracketed by barrier + synchronize, CUDA events on the current stream; returns
+    milliseconds (max over ranks).  After the barrier a rank has waited for the slowest one with an idle
+    GPU, so LEAD_IN more untimed calls run first and the start event is recorded behind them, in stream
+    order: the K timed calls start on a busy, clocked-up GPU with the host already ahead, as they do in
+    the middle of a run -- with only 20 timed steps the ramp-up of an idle GPU was 3-9 % of the window."""
     import torch
     import torch.distributed as dist
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize(device)
+    for _ in range(LEAD_IN):
+        fn()
     e0.record()
     for _ in range(steps):
         fn()
@@ -637,6 +645,8 @@ def run_gpu(args):
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(world, n, nseg, total),
         "impl_notes": {"noise": "in-kernel Philox4x32-10 + Box-Muller",
+                       "timing": f"W warm-up steps; barrier + synchronize; {LEAD_IN} more untimed steps; start event; K timed steps; "
+                                 "stop event; synchronize; max over ranks",
                        "l2": "consecutive launches walk the chain in opposite directions, so each starts on the lines "
                              "the previous one left in L2 (roofline.frac); roofline.production evicts the L2 in between",
                        "host_us_per_step": host_us},
