@@ -163,6 +163,17 @@ class EvalAccumulators:
         return self.out_host.tolist(), probs
 
 
+_CALIBRATION = None
+
+
+def set_calibration_metrics(ece, ace, rmsce) -> None:
+    """The three functions `evaluate_model(..., calibration_eval=True)` applies to (labels, ensemble
+    probabilities): the reference imports them into exp_utils (exp_utils.py:13) from its third-party
+    module; this package neither ships nor imports them."""
+    global _CALIBRATION
+    _CALIBRATION = (ece, ace, rmsce)
+
+
 def evaluate_model(model, dataloader_test: Iterable[Tuple[torch.Tensor, torch.Tensor]],
                    samples: Dict[str, torch.Tensor],
                    likelihood_eval: bool, accuracy_eval: bool, calibration_eval: bool):
@@ -239,13 +250,14 @@ def evaluate_model(model, dataloader_test: Iterable[Tuple[torch.Tensor, torch.Te
         results["acc_last"] = out[N.EV_ACC_LAST]
     if calibration_eval:
         # the binning metrics are the reference's third-party numpy code (third_party/
-        # calibration_error.py, a TensorFlow-Probability derivative); they run on the ensemble
-        # probabilities this evaluation produced on the device
-        try:
-            from bnn_priors.third_party.calibration_error import ace, ece, rmsce
-        except ImportError as e:
-            raise RuntimeError("calibration_eval=True needs the reference's "
-                               "bnn_priors.third_party.calibration_error on the path") from e
+        # calibration_error.py, a TensorFlow-Probability derivative), out of this path's scope: the
+        # caller hands them over (overlay.install(evaluate=True) does, from the reference's exp_utils);
+        # they run on the ensemble probabilities this evaluation produced on the device
+        if _CALIBRATION is None:
+            raise RuntimeError("calibration_eval=True: hand the calibration metrics over first with "
+                               "evaluate.set_calibration_metrics(ece, ace, rmsce) "
+                               "(overlay.install(evaluate=True) does it with the reference's own)")
+        ece, ace, rmsce = _CALIBRATION
         probs_mean = probs.cpu().numpy()
         labels_np = labels.cpu().numpy()
         results["ece"] = float(ece(labels_np, probs_mean).mean())

@@ -44,7 +44,11 @@ _EVAL_MODULES = ("exp_utils", "inference", "inference_reject")
 
 
 def _install_evaluate(pkg: str) -> None:
+    from . import evaluate as _ev
     from .evaluate import evaluate_model as fast_eval
+    eu = sys.modules.get(f"{pkg}.exp_utils")
+    if eu is not None and all(hasattr(eu, n) for n in ("ece", "ace", "rmsce")):
+        _ev.set_calibration_metrics(eu.ece, eu.ace, eu.rmsce)      # exp_utils.py:13
     saved = _saved.setdefault("evaluate", {})
     for sub in _EVAL_MODULES:
         name = f"{pkg}.{sub}"

@@ -213,3 +213,34 @@ def test_errors():
         dataset = object()
     with pytest.raises(ValueError, match="cannot find the labels"):
         evaluate_model(model, NoLabels(), {}, True, True, False)
+
+
+def test_calibration_metrics_through_the_overlay_match_the_reference():
+    """calibration_eval=True: the binning metrics are the reference's third-party code, handed over by
+    overlay.install(evaluate=True); same numbers as the reference's evaluate_model on its own model."""
+    import refenv
+    if not refenv.available():
+        pytest.skip("no oracle/_ref snapshot")
+    eu = refenv.exp_utils()
+    from bnn_priors_b200 import evaluate as EV, overlay
+    data = refenv.synthetic_dataset("mnist", torch.device(DEV), 64, 300, seed=3)
+    model = refenv.build_model("densenet_gaussian", data, seed=3)
+    loader = torch.utils.data.DataLoader(data.norm.test, batch_size=128)
+    sd = model.state_dict()
+    g = torch.Generator(device=DEV).manual_seed(0)
+    samples = {k: torch.stack([v + 0.05 * i * torch.randn(v.shape, device=v.device, generator=g) if v.dtype.is_floating_point else v
+                               for i in range(3)]) for k, v in sd.items()}
+    ref_eval = eu.evaluate_model
+    want = ref_eval(model, loader, samples, likelihood_eval=True, accuracy_eval=True, calibration_eval=True)
+    EV._CALIBRATION = None
+    with pytest.raises(RuntimeError, match="set_calibration_metrics"):
+        EV.evaluate_model(model, loader, samples, True, True, True)
+    overlay.install(evaluate=True)
+    try:
+        assert eu.evaluate_model is EV.evaluate_model
+        got = eu.evaluate_model(model, loader, samples, likelihood_eval=True, accuracy_eval=True, calibration_eval=True)
+    finally:
+        overlay.uninstall()
+    assert set(got) == set(want) == {"lp_ensemble", "lp_last", "acc_ensemble", "acc_last", "ece", "ace", "rmsce"}
+    for k in want:
+        assert got[k] == pytest.approx(want[k], rel=2e-6, abs=1e-7), k
