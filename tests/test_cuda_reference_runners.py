@@ -14,6 +14,8 @@ gaussian, (3) convnet / VerletSGLDReject / laplace / T=0.1, (4) googleresnet / V
 student-t, (5) HMC with 50 leapfrog steps / googleresnet / gaussian, (1) densenet / SGLD.
 """
 import importlib
+import json
+import os
 import warnings
 
 import pytest
@@ -44,6 +46,10 @@ CASES = {
 def _check(report, tape, runner_a, runner_b, name):
     d = report.as_dict()
     print(f"\n[{name}] calls={tape.summary()} report={d}")
+    if os.environ.get("BNNP_REPORT_FILE"):           # tools/gpu_session.sh keeps the numbers for profiles/
+        with open(os.environ["BNNP_REPORT_FILE"], "a") as f:
+            f.write(json.dumps(dict(case=name, calls=tape.summary(), **{k: (v if v != float("inf") else None)
+                                                                        for k, v in d.items()})) + "\n")
     assert report.n_events == len(tape.events)
     assert report.p_err <= TOL, d
     assert report.m_err <= TOL, d

@@ -7,7 +7,7 @@ mkdir -p $out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > $out/${tag}_clocks.csv 2>/dev/null &
 smi=$!
 if [ "$2" != "skip-tests" ]; then
-  python -m pytest tests -q -m gpu -p no:cacheprovider > $out/${tag}_gpu_tests.log 2>&1
+  BNNP_REPORT_FILE=$PWD/$out/${tag}_parity_reports.jsonl python -m pytest tests -q -m gpu -p no:cacheprovider > $out/${tag}_gpu_tests.log 2>&1
   tail -25 $out/${tag}_gpu_tests.log
 fi
 python bench.py --steps 200 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err || tail -20 $out/${tag}_bench.err
@@ -15,6 +15,8 @@ python bench.py --steps 20 --warmup 5 --no-extra --no-cpu > $out/${tag}_bench_20
 python bench.py --impl reference --steps 20 --warmup 5 > $out/${tag}_bench_reference_arm.json 2> $out/${tag}_bench_ref.err || tail -5 $out/${tag}_bench_ref.err
 python tools/bench_small_models.py > $out/${tag}_small_models.json 2> $out/${tag}_small_models.err || tail -5 $out/${tag}_small_models.err
 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; tail -2 $out/${tag}_smoke.log
+python tools/variant_times.py > $out/${tag}_variants.jsonl 2>> $out/${tag}_small_models.err
+python tools/tune_tiles.py > $out/${tag}_tune.json 2>> $out/${tag}_small_models.err
 kill $smi 2>/dev/null
 # ---- ncu: launch list of the bench command (shares of the step), then the kernels themselves
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv \
