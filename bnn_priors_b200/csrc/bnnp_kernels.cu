@@ -723,10 +723,126 @@ __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCt
 #ifndef BNNP_PRIOR_MIN_CTAS
 #define BNNP_PRIOR_MIN_CTAS BNNP_MIN_CTAS
 #endif
+
+// ---------------------------------------------------------------------------------
+// TMA staging (variants with more arithmetic per element).  A full chunk of a launch that reads all
+// three streams is fetched by ONE thread with three 16 KB bulk copies (cp.async.bulk global -> shared,
+// completion on an mbarrier) instead of twelve 128-bit loads per thread held in 48 registers: the
+// threads then take one quad at a time out of shared memory, so the fused-prior and all-sums variants
+// neither spill nor carry the 64-bit address arithmetic and predicates of the per-thread loads --
+// they are issue-bound, not memory-bound (profiles/r02_ncu_variants.json).  Measured (profiles/r02_notes.md,
+// production regime): metrics step 81.2 -> 78.5 us (back to 4 CTAs/SM), Verlet + fused prior 81.7 -> 80.9,
+// Verlet + fused prior + metrics 91.0 -> 83.6; the lean variants gain nothing and keep the register path.
+// ---------------------------------------------------------------------------------
+#ifndef BNNP_TMA_MODE
+#define BNNP_TMA_MODE 2     // 0: never; 1: every variant without a replay buffer; 2: fused-prior and all-sums variants
+#endif
+constexpr int TMA_STREAM_BYTES = CHUNK * 4;
+constexpr int TMA_SMEM_BYTES = 3 * TMA_STREAM_BYTES + 16;       // three staged streams + the mbarrier
+
+template <int NOISE, bool PRIOR, int SUMS>
+__host__ __device__ constexpr bool use_tma() {
+    return NOISE != BNNP_NOISE_REPLAY &&
+           (BNNP_TMA_MODE == 1 || (BNNP_TMA_MODE == 2 && (PRIOR || SUMS == 2)));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n"
+                     "}"
+                     : "=r"(done)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar), "l"(pol)
+                 : "memory");
+}
+
+// process_chunk for a chunk staged in shared memory: one quad of every stream at a time
+template <int NOISE, bool PRIOR, int KIND, bool NOISE_FIRST, int SUMS>
+__device__ __forceinline__ void process_staged(const BnnpLaunch& L, const ChunkCtx& cx, const Coef& c, const PriorConst& pc,
+                                               const PhiloxKeys& keys, const float* sP, const float* sG, const float* sM,
+                                               float acc[BNNP_NRED], const uint32_t flags, const uint64_t call) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int e = (u * THREADS + cx.tid) * 4;
+        const int64_t fi = cx.fbase + e;
+        F4 p, g, m, z;
+        p.v = *reinterpret_cast<const float4*>(sP + e);
+        g.v = *reinterpret_cast<const float4*>(sG + e);
+        m.v = *reinterpret_cast<const float4*>(sM + e);
+        z.v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (flags & BNNP_F_SAVE_STATE) {   // verlet_sgld.py:72-83, the values BEFORE the update
+            st_f4_hint(L.prev_p + fi, p.v, POLICY_EVICT_FIRST);
+            st_f4_hint(L.prev_g + fi, g.v, POLICY_EVICT_FIRST);
+            if (L.prev_m != nullptr) st_f4_hint(L.prev_m + fi, m.v, POLICY_EVICT_FIRST);
+        }
+        if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)fi >> 2, call, keys, z.f);
+        update_quad<NOISE, PRIOR, KIND, NOISE_FIRST, SUMS, true>(flags, c, pc, 4, p, g, m, z.f, acc);
+        if (flags & BNNP_F_WRITE_P) st_state(L.P + fi, p.v);
+        if (flags & BNNP_F_WRITE_M) st_state(L.M + fi, m.v);
+    }
+}
+
+template <int NOISE, bool PRIOR, bool NOISE_FIRST, int SUMS>
+__device__ __forceinline__ void staged_body(const BnnpLaunch& L, const PhiloxKeys& keys, const Dyn& dyn, const ChunkCtx& cx,
+                                            const Coef& c, const BnnpSegment& sd, int seg, const float* sP, const float* sG,
+                                            const float* sM, float acc[BNNP_NRED]) {
+    const uint32_t flags = dyn.flags;
+    if (PRIOR) {
+        float hyper_term = 0.0f;
+        if (is_hyper_kind(sd.prior_kind)) hyper_term = (float)L.seg_state[(int64_t)seg * BNNP_STATE_STRIDE + BNNP_S_HYPER];
+#define BNNP_FORM_CASE(F)                                                                                       \
+    case F:                                                                                                     \
+        process_staged<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, dyn.inv_n, hyper_term), keys, sP, sG, \
+                                                          sM, acc, flags, dyn.call);                            \
+        break;
+        switch (prior_form(sd.prior_kind)) {
+            BNNP_FORM_CASE(F_NORMAL)
+#ifndef BNNP_ONLY_NORMAL
+            BNNP_FORM_CASE(F_LOGNORMAL)
+            BNNP_FORM_CASE(F_LAPLACE)
+            BNNP_FORM_CASE(F_STUDENT_T)
+            BNNP_FORM_CASE(F_GENNORM)
+            BNNP_FORM_CASE(F_DOUBLE_GAMMA)
+#endif
+            BNNP_FORM_CASE(F_CONST)
+            BNNP_FORM_CASE(F_NONE)
+        }
+#undef BNNP_FORM_CASE
+    } else {
+        process_staged<NOISE, false, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, PriorConst(), keys, sP, sG, sM, acc, flags, dyn.call);
+    }
+}
+
+#ifndef BNNP_TMA_ALLSUMS_CTAS
+#define BNNP_TMA_ALLSUMS_CTAS 4     // the all-sums variants fit 64 registers once the streams are staged in shared memory
+#endif
 template <int NOISE, int SUMS, bool PRIOR>
 constexpr int min_ctas() {
     return (NOISE != BNNP_NOISE_REPLAY && SUMS != 2) ? (PRIOR ? BNNP_PRIOR_MIN_CTAS : BNNP_MIN_CTAS)
-                                                     : (BNNP_MIN_CTAS > 3 ? 3 : BNNP_MIN_CTAS);
+           : (use_tma<NOISE, PRIOR, SUMS>()          ? BNNP_TMA_ALLSUMS_CTAS
+                                                     : (BNNP_MIN_CTAS > 3 ? 3 : BNNP_MIN_CTAS));
 }
 
 #ifndef BNNP_FULL_MODE
@@ -805,9 +921,25 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     const int chunk = L.chunk_ids != nullptr ? L.chunk_ids[slot] : slot;
     const ChunkDesc cd = load_chunk(L.chunks, chunk);
     const int seg = cd.seg;
+    constexpr uint32_t READ_ALL = BNNP_F_READ_P | BNNP_F_READ_G | BNNP_F_READ_M;
+    constexpr bool TMA = use_tma<NOISE, PRIOR, SUMS>();
+    const bool full = cd.rem == CHUNK && (flags & READ_ALL) == READ_ALL;
+    extern __shared__ __align__(128) unsigned char bnnp_dsm[];
+    float* const sP = reinterpret_cast<float*>(bnnp_dsm);
+    float* const sG = sP + CHUNK;
+    float* const sM = sG + CHUNK;
+    const uint32_t mbar = smem_u32(sM + CHUNK);
+    if (TMA && full && tid == 0) {
+        // P and M do not wait for the segment descriptor: their bulk copies go out first
+        mbar_init(mbar, 1);
+        mbar_arrive_expect_tx(mbar, 3 * TMA_STREAM_BYTES);
+        bulk_g2s_hint(smem_u32(sP), L.P + cd.fbase, TMA_STREAM_BYTES, mbar, POLICY_EVICT_LAST);
+        bulk_g2s_hint(smem_u32(sM), L.M + cd.fbase, TMA_STREAM_BYTES, mbar, POLICY_EVICT_LAST);
+    }
     const BnnpSegment sd = L.segs[seg];
     // the segment's gradient: its slice of the flat G, or the tensor autograd handed over
     const float* gsrc = L.seg_grad != nullptr ? L.seg_grad[seg] + (cd.fbase - sd.off) : L.G + cd.fbase;
+    if (TMA && full && tid == 0) bulk_g2s(smem_u32(sG), gsrc, TMA_STREAM_BYTES, mbar);
     // the previous launch's bookkeeping: segment j is handled by CTA j, i.e. by the CTAs that
     // start first, so the few microseconds it takes are absorbed at the front of the launch
     if ((int)blockIdx.x < L.nseg) {
@@ -830,16 +962,21 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
 #pragma unroll
     for (int k = 0; k < BNNP_NRED; ++k) acc[k] = 0.0f;
 
-    // Nearly every chunk is a full one of a launch that reads all three streams: that case runs without
-    // the per-quad bounds / flag tests and without the zero fill (FULL), the rest (the last chunk of a
-    // tensor, launches that skip a stream) takes the general path.
-    constexpr uint32_t READ_ALL = BNNP_F_READ_P | BNNP_F_READ_G | BNNP_F_READ_M;
-    // (measured per variant, profiles/r02_notes.md: the split pays for the variants that reduce every sum)
-    constexpr bool SPLIT = BNNP_FULL_MODE == 1 || (BNNP_FULL_MODE == 2 && SUMS == SUMS_ALL);
-    if (SPLIT && cx.rem == CHUNK && (flags & READ_ALL) == READ_ALL)
-        chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, true>(L, keys, dyn, cx, c, sd, seg, gsrc, acc);
-    else
-        chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, false>(L, keys, dyn, cx, c, sd, seg, gsrc, acc);
+    if (TMA && full) {
+        __syncthreads();                 // the mbarrier thread 0 initialised is visible to everybody
+        mbar_wait(mbar, 0);
+        staged_body<NOISE, PRIOR, NOISE_FIRST, SUMS>(L, keys, dyn, cx, c, sd, seg, sP, sG, sM, acc);
+    } else {
+        // Nearly every chunk is a full one of a launch that reads all three streams: that case can run
+        // without the per-quad bounds / flag tests and without the zero fill (FULL), the rest (the last
+        // chunk of a tensor, launches that skip a stream) takes the general path.
+        // (measured per variant, profiles/r02_notes.md: the split pays for the variants that reduce every sum)
+        constexpr bool SPLIT = !TMA && (BNNP_FULL_MODE == 1 || (BNNP_FULL_MODE == 2 && SUMS == SUMS_ALL));
+        if (SPLIT && full)
+            chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, true>(L, keys, dyn, cx, c, sd, seg, gsrc, acc);
+        else
+            chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, false>(L, keys, dyn, cx, c, sd, seg, gsrc, acc);
+    }
 
     // ---- chunk reduction: fp32 butterfly inside the warp, fp64 across warps (fixed order)
     constexpr unsigned LIVE = (SUMS == SUMS_ALL) ? 0xffu
@@ -1110,6 +1247,26 @@ StepKernel pick_kernel(int noise, bool prior, bool noise_first, int sums) {
 
 bool misaligned(const void* p) { return ((uintptr_t)p & 15u) != 0; }
 
+bool variant_uses_tma(int noise, bool prior, int sums) {
+    return noise != BNNP_NOISE_REPLAY && (BNNP_TMA_MODE == 1 || (BNNP_TMA_MODE == 2 && (prior || sums == 2)));
+}
+
+// dynamic shared memory of a step-kernel instantiation (the TMA-staged variants need 48 KB + 16 B, above the
+// default limit: the attribute is set once per instantiation and device)
+int step_kernel_smem(StepKernel k, int noise, bool prior, int sums) {
+    if (!variant_uses_tma(noise, prior, sums)) return 0;
+    static thread_local const void* done[64];
+    static thread_local int ndone = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void* tag = (const void*)((uintptr_t)(const void*)k ^ ((uintptr_t)dev << 56));
+    for (int i = 0; i < ndone; ++i)
+        if (done[i] == tag) return TMA_SMEM_BYTES;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES) != cudaSuccess) return -1;
+    if (ndone < 64) done[ndone++] = tag;
+    return TMA_SMEM_BYTES;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1130,7 +1287,9 @@ int bnnp_device_info(int device, int* sm_count, int* l2_bytes) {
 int bnnp_max_ctas_per_sm(int noise, int has_prior, int noise_first, int sums, int* out) {
     StepKernel k = pick_kernel(noise, has_prior != 0, noise_first != 0, sums);
     if (k == nullptr || out == nullptr) return fail(BNNP_E_ARG, "bnnp_max_ctas_per_sm: bad variant");
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, THREADS, 0);
+    const int smem = step_kernel_smem(k, noise, has_prior != 0, sums);
+    if (smem < 0) return fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, THREADS, smem);
     if (e != cudaSuccess) return fail_cuda(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     return 0;
 }
@@ -1222,7 +1381,9 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
     sp.cm = (float)a->cm;
     sp.cn = (float)a->cn;
     sp.gmax = (float)a->grad_max;
-    k<<<a->nchunks, THREADS, 0, (cudaStream_t)stream>>>(sp);
+    const int smem = (f & BNNP_F_HYPER) ? 0 : step_kernel_smem(k, a->noise, prior, sums_needed(a->op, f));
+    if (smem < 0) return fail_cuda(cudaGetLastError(), "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    k<<<a->nchunks, THREADS, smem, (cudaStream_t)stream>>>(sp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "bnnp_step_kernel launch");
     return 0;
