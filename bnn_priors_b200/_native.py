@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BNNP_LIB") or os.path.join(HERE, "_lib", "libbnnp.so")
 
 # ---- constants of include/bnnp.h (tests/test_abi.py checks them against the header)
-ABI_VERSION = 9
+ABI_VERSION = 10
 SEG_ALIGN = 32
 THREADS = 256
 UNROLL = 4
@@ -48,6 +48,7 @@ F_ALL_SUMS = 1 << 13
 F_HYPER = 1 << 14
 F_REVERSE = 1 << 15
 F_HYPER_POST = 1 << 16
+F_HYPER_CHAIN = 1 << 17
 
 (S_DELTA_ENERGY, S_PREV_NEW_MOM, S_EST_MM, S_EST_PG, S_SUM_GG, S_SUM_MM, S_SQ_MEAN,
  S_LOG_PRIOR, S_GM_OLD, S_GM_NEW, S_MM_OLD, S_MM_NEW, S_NONFINITE, S_LAUNCHES, S_HYPER) = range(15)

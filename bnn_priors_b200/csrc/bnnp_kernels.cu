@@ -223,12 +223,16 @@ __device__ __forceinline__ float hyper_scale_f32(const BnnpSegment& h, float u) 
     return h.prior_kind == BNNP_PRIOR_HYPER_HALFCAUCHY ? sp * h.prior_scale : sp;
 }
 
+// `scale_free_log`: a NORMAL / LAPLACE segment with a sampled scale in a BNNP_F_HYPER_POST launch reduces
+// sum(-d^2/2) resp. sum(-|d|) in the log-prior slot -- the statistic its hyper segment needs, independent
+// of the scale this launch used -- instead of the log-density terms.
 template <int FORM>
-__device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double inv_n, float hyper_term) {
+__device__ __forceinline__ PriorConst make_prior(const BnnpSegment& sd, double inv_n, float hyper_term,
+                                                 bool scale_free_log = false) {
     PriorConst pc;
     pc.loc = sd.prior_loc;
     const float s = sd.prior_scale;
-    pc.inv_s = 1.0f / s;
+    pc.inv_s = scale_free_log ? 1.0f : 1.0f / s;
     pc.k = (float)inv_n;
     pc.c = pc.a = pc.b = pc.la = pc.inv_df = 0.0f;
     if (FORM == F_NORMAL || FORM == F_LOGNORMAL) {
@@ -490,11 +494,53 @@ __host__ __device__ inline int sums_needed(int op, uint32_t flags) {
     return op == BNNP_OP_VERLET ? SUMS_VERLET : SUMS_MIN;
 }
 
-// The reference's per-tensor scalar bookkeeping for one segment and one launch `E`,
-// applied to the segment-state array (fp64) from the eight folded sums `r`.
-// Epilogue of the hierarchical-prior pre-pass (BNNP_F_HYPER) for one segment.
-//   hyper segment h (link = weight segment w): from u = P[off_h] and the statistic T of w
-//   (folded into r[BNNP_NRED] by apply_pending):
+// What a hyper segment needs from its own value u and the statistic T of the segment it scales:
+// the scale, its log density, -(1/N) d/du [ sum_i log p(w_i | s(u)) + log p_hyper(s(u)) ].
+struct HyperValues {
+    double s, lp, grad;
+};
+__device__ HyperValues hyper_values(const BnnpSegment& h, const BnnpSegment& w, double u, double T, double inv_num_data) {
+    HyperValues v;
+    double ds;
+    hyper_scale(h, u, v.s, ds);
+    const double s = v.s;
+    const double a = (double)h.prior_loc, b = (double)h.prior_scale;
+    double lp = 0.0, dlp = 0.0;
+    if (h.prior_kind == BNNP_PRIOR_HYPER_GAMMA) {               // td.Gamma(a, b).log_prob(s)
+        lp = a * log(b) + (a - 1.0) * log(s) - b * s - lgamma(a);
+        dlp = ((a - 1.0) / s - b) * ds;
+    } else if (h.prior_kind == BNNP_PRIOR_HYPER_UNIFORM) {      // -log(high - low)
+        lp = -log(b);
+    } else if (h.prior_kind == BNNP_PRIOR_HYPER_HALFCAUCHY) {   // td.HalfCauchy(a).log_prob(s)
+        const double q = s / a;
+        lp = -0.4515827052894548 /* log(2/pi) */ - log(a) - log1p(q * q);
+        dlp = -(2.0 * q / a) / (1.0 + q * q) * ds;
+    }
+    const double n = (double)w.numel, df = (double)w.prior_df;
+    double dl_ds = 0.0;                                          // sum_i d log p(w_i | s) / ds
+    if (w.prior_kind == BNNP_PRIOR_NORMAL) dl_ds = T / (s * s * s) - n / s;
+    else if (w.prior_kind == BNNP_PRIOR_LAPLACE) dl_ds = T / (s * s) - n / s;
+    else if (w.prior_kind == BNNP_PRIOR_STUDENT_T) dl_ds = (df + 1.0) * T / s - n / s;
+    v.lp = lp;
+    v.grad = -inv_num_data * (dl_ds * ds + dlp);
+    return v;
+}
+
+// BNNP_F_HYPER_POST: the value u' the launch `E` left in hyper segment `h`.  That launch's hyper CTA stashed
+// it in the R_LOGP slot of its chunk's partial record (a hyper segment has no log-density term of its own
+// there), where it stays put while the NEXT launch already rewrites P.
+__device__ __forceinline__ double stashed_u(const BnnpLaunch& L, const BnnpEpilogue& E, const BnnpSegment& h) {
+    return ld_cg_f64(L.partials + ((int64_t)E.parity * L.nchunks_total + h.first_chunk) * BNNP_NRED + R_LOGP);
+}
+// ... and the scale-free statistic of the segment it scales, from that launch's folded R_LOGP sum:
+// the launch reduced sum(-d^2/2) (NORMAL) or sum(-|d|) (LAPLACE) for linked segments
+__device__ __forceinline__ double post_statistic(const BnnpSegment& w, double folded) {
+    return w.prior_kind == BNNP_PRIOR_NORMAL ? -2.0 * folded : -folded;
+}
+
+// Epilogue of the hierarchical-prior pre-pass (BNNP_F_HYPER) or of a BNNP_F_HYPER_POST step for one segment.
+//   hyper segment h (link = weight segment w): from u and the statistic T of w (folded into r[BNNP_NRED]
+//   by apply_pending):
 //     BNNP_S_LOG_PRIOR <- log density of the scale           (scale_prior.log_prob())
 //     BNNP_S_HYPER     <- -(1/N) d/du [ sum_i log p(w_i | s(u)) + log p_hyper(s(u)) ]
 //     segs[w].prior_scale <- s(u)                            (what scale_prior() returns)
@@ -502,38 +548,17 @@ __host__ __device__ inline int sums_needed(int op, uint32_t flags) {
 __device__ void hyper_epilogue(const BnnpLaunch& L, const BnnpEpilogue& E, const BnnpSegment& sd, double* st,
                                const double* r) {
     if (sd.link < 0 || sd.link >= L.nseg) return;
-    // BNNP_F_HYPER_POST: the launch was a step; r[BNNP_NRED] is the linked segment's sum of log-density
-    // terms at the parameters now in P, evaluated with the scale the table held during the launch
+    // BNNP_F_HYPER_POST: the launch was a step; r[BNNP_NRED] is the linked segment's folded R_LOGP sum at the
+    // parameters that launch left in P
     const bool post = (E.flags & BNNP_F_HYPER_POST) != 0;
     if (is_hyper_kind(sd.prior_kind)) {
         const BnnpSegment w = L.segs[sd.link];
-        const double u = (double)L.P[sd.off];
-        double s, ds;
-        hyper_scale(sd, u, s, ds);
-        const double a = (double)sd.prior_loc, b = (double)sd.prior_scale;
-        double lp = 0.0, dlp = 0.0;
-        if (sd.prior_kind == BNNP_PRIOR_HYPER_GAMMA) {               // td.Gamma(a, b).log_prob(s)
-            lp = a * log(b) + (a - 1.0) * log(s) - b * s - lgamma(a);
-            dlp = ((a - 1.0) / s - b) * ds;
-        } else if (sd.prior_kind == BNNP_PRIOR_HYPER_UNIFORM) {      // -log(high - low)
-            lp = -log(b);
-        } else if (sd.prior_kind == BNNP_PRIOR_HYPER_HALFCAUCHY) {   // td.HalfCauchy(a).log_prob(s)
-            const double q = s / a;
-            lp = -0.4515827052894548 /* log(2/pi) */ - log(a) - log1p(q * q);
-            dlp = -(2.0 * q / a) / (1.0 + q * q) * ds;
-        }
-        const double n = (double)w.numel, df = (double)w.prior_df;
-        double T = r[BNNP_NRED];
-        if (post) {
-            const double s_old = (double)w.prior_scale;              // nobody else writes it
-            T = w.prior_kind == BNNP_PRIOR_NORMAL ? -2.0 * s_old * s_old * T : -s_old * T;
-        }
-        double dl_ds = 0.0;                                          // sum_i d log p(w_i | s) / ds
-        if (w.prior_kind == BNNP_PRIOR_NORMAL) dl_ds = T / (s * s * s) - n / s;
-        else if (w.prior_kind == BNNP_PRIOR_LAPLACE) dl_ds = T / (s * s) - n / s;
-        else if (w.prior_kind == BNNP_PRIOR_STUDENT_T) dl_ds = (df + 1.0) * T / s - n / s;
-        st[BNNP_S_LOG_PRIOR] = lp;
-        st[BNNP_S_HYPER] = -E.inv_num_data * (dl_ds * ds + dlp);
+        const double u = post ? stashed_u(L, E, sd) : (double)L.P[sd.off];
+        const double T = post ? post_statistic(w, r[BNNP_NRED]) : r[BNNP_NRED];
+        const HyperValues v = hyper_values(sd, w, u, T, E.inv_num_data);
+        const double s = v.s, n = (double)w.numel;
+        st[BNNP_S_LOG_PRIOR] = v.lp;
+        st[BNNP_S_HYPER] = v.grad;
         if (post) {
             // the linked segment's log-prior at the new parameters AND the new scale
             double* st_w = L.seg_state + (int64_t)sd.link * BNNP_STATE_STRIDE;
@@ -555,6 +580,8 @@ __device__ void hyper_epilogue(const BnnpLaunch& L, const BnnpEpilogue& E, const
     }
 }
 
+// The reference's per-tensor scalar bookkeeping for one segment and one launch `E`,
+// applied to the segment-state array (fp64) from the eight folded sums `r`.
 __device__ void segment_epilogue(const BnnpEpilogue& E, double* seg_state, const BnnpSegment& sd, int seg,
                                  const double* r) {
     const uint32_t flags = E.flags;
@@ -806,16 +833,14 @@ __device__ __forceinline__ void process_staged(const BnnpLaunch& L, const ChunkC
 
 template <int NOISE, bool PRIOR, bool NOISE_FIRST, int SUMS>
 __device__ __forceinline__ void staged_body(const BnnpLaunch& L, const PhiloxKeys& keys, const Dyn& dyn, const ChunkCtx& cx,
-                                            const Coef& c, const BnnpSegment& sd, int seg, const float* sP, const float* sG,
-                                            const float* sM, float acc[BNNP_NRED]) {
+                                            const Coef& c, const BnnpSegment& sd, float hyper_term, bool scale_free,
+                                            const float* sP, const float* sG, const float* sM, float acc[BNNP_NRED]) {
     const uint32_t flags = dyn.flags;
     if (PRIOR) {
-        float hyper_term = 0.0f;
-        if (is_hyper_kind(sd.prior_kind)) hyper_term = (float)L.seg_state[(int64_t)seg * BNNP_STATE_STRIDE + BNNP_S_HYPER];
 #define BNNP_FORM_CASE(F)                                                                                       \
     case F:                                                                                                     \
-        process_staged<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, dyn.inv_n, hyper_term), keys, sP, sG, \
-                                                          sM, acc, flags, dyn.call);                            \
+        process_staged<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, dyn.inv_n, hyper_term, scale_free), \
+                                                          keys, sP, sG, sM, acc, flags, dyn.call);              \
         break;
         switch (prior_form(sd.prior_kind)) {
             BNNP_FORM_CASE(F_NORMAL)
@@ -851,8 +876,8 @@ constexpr int min_ctas() {
 // Loads, noise, prior, update and stores of one chunk; the partial sums come back in `acc`.
 template <int NOISE, bool PRIOR, bool NOISE_FIRST, int SUMS, bool FULL>
 __device__ __forceinline__ void chunk_body(const BnnpLaunch& L, const PhiloxKeys& keys, const Dyn& dyn, const ChunkCtx& cx,
-                                           const Coef& c, const BnnpSegment& sd, int seg, const float* gsrc,
-                                           float acc[BNNP_NRED]) {
+                                           const Coef& c, const BnnpSegment& sd, float hyper_term, bool scale_free,
+                                           const float* gsrc, float acc[BNNP_NRED]) {
     const uint32_t flags = dyn.flags;
     const int tid = cx.tid;
     // ---- front-batched 128-bit loads: 3 (4 with replay noise) x UNROLL in flight per thread
@@ -878,15 +903,9 @@ __device__ __forceinline__ void chunk_body(const BnnpLaunch& L, const PhiloxKeys
     }
 
     if (PRIOR) {
-        float hyper_term = 0.0f;
-        if (is_hyper_kind(sd.prior_kind)) {
-            // -(1/N) d log p / du, left by the epilogue of the BNNP_F_HYPER pre-pass (finalised before
-            // this launch started: bnnp_launch refuses a pending BNNP_F_HYPER epilogue)
-            hyper_term = (float)L.seg_state[(int64_t)seg * BNNP_STATE_STRIDE + BNNP_S_HYPER];
-        }
 #define BNNP_FORM_CASE(F)                                                                                      \
     case F:                                                                                                    \
-        process_chunk<NOISE, true, F, NOISE_FIRST, SUMS, FULL>(L, cx, c, make_prior<F>(sd, dyn.inv_n, hyper_term), \
+        process_chunk<NOISE, true, F, NOISE_FIRST, SUMS, FULL>(L, cx, c, make_prior<F>(sd, dyn.inv_n, hyper_term, scale_free), \
                                                                keys, p, g, m, z, acc, flags, dyn.call);        \
         break;
         switch (prior_form(sd.prior_kind)) {   // uniform over the CTA: one closed form per segment
@@ -936,10 +955,53 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
         bulk_g2s_hint(smem_u32(sP), L.P + cd.fbase, TMA_STREAM_BYTES, mbar, POLICY_EVICT_LAST);
         bulk_g2s_hint(smem_u32(sM), L.M + cd.fbase, TMA_STREAM_BYTES, mbar, POLICY_EVICT_LAST);
     }
-    const BnnpSegment sd = L.segs[seg];
+    BnnpSegment sd = L.segs[seg];
     // the segment's gradient: its slice of the flat G, or the tensor autograd handed over
     const float* gsrc = L.seg_grad != nullptr ? L.seg_grad[seg] + (cd.fbase - sd.off) : L.G + cd.fbase;
     if (TMA && full && tid == 0) bulk_g2s(smem_u32(sG), gsrc, TMA_STREAM_BYTES, mbar);
+
+    // Sampled scales (hierarchical priors).  Normally the table holds the current scale of a linked segment
+    // and the segment state the hyper-parameter's gradient term (left by the epilogue of a pre-pass or of
+    // a BNNP_F_HYPER_POST step, finalised before this launch).  BNNP_F_HYPER_CHAIN: that epilogue is still
+    // PENDING -- it rides on this launch like any other epilogue -- so the CTAs that need its results
+    // derive them themselves from the pending launch's records: a linked segment its scale from the stashed
+    // hyper-parameter, a hyper segment its gradient term from the folded statistic.  The CTA that applies
+    // the epilogue (blockIdx = segment) writes the same values for the host; nobody waits for anybody.
+    float hyper_term = 0.0f;
+    bool scale_free = false;
+    if (PRIOR) {
+        __shared__ double s_chain[2];
+        const bool linked = sd.link >= 0 && sd.link < L.nseg;
+        const bool chain = (flags & BNNP_F_HYPER_CHAIN) != 0;
+        scale_free = (flags & BNNP_F_HYPER_POST) && linked && may_have_hyper_scale(sd.prior_kind) &&
+                     sd.prior_kind != BNNP_PRIOR_STUDENT_T;
+        if (chain && linked && may_have_hyper_scale(sd.prior_kind)) {
+            if (tid == 0) {
+                const BnnpEpilogue E = load_pending(L);
+                const BnnpSegment h = L.segs[sd.link];
+                double sc, ds;
+                hyper_scale(h, stashed_u(L, E, h), sc, ds);
+                s_chain[0] = sc;
+            }
+            __syncthreads();
+            sd.prior_scale = (float)s_chain[0];
+        } else if (is_hyper_kind(sd.prior_kind)) {
+            if (chain && linked) {
+                const BnnpEpilogue E = load_pending(L);
+                const BnnpSegment w = L.segs[sd.link];
+                if (tid < 32) {
+                    const double t = fold_records(L.partials + ((int64_t)E.parity * L.nchunks_total + w.first_chunk) * BNNP_NRED + R_LOGP,
+                                                  w.num_chunks, tid);
+                    if (tid == 0) s_chain[1] = hyper_values(sd, w, stashed_u(L, E, sd), post_statistic(w, t), E.inv_num_data).grad;
+                }
+                __syncthreads();
+                hyper_term = (float)s_chain[1];
+            } else {
+                // -(1/N) d log p / du, left in the segment state by an epilogue that has been applied
+                hyper_term = (float)L.seg_state[(int64_t)seg * BNNP_STATE_STRIDE + BNNP_S_HYPER];
+            }
+        }
+    }
     // the previous launch's bookkeeping: segment j is handled by CTA j, i.e. by the CTAs that
     // start first, so the few microseconds it takes are absorbed at the front of the launch
     if ((int)blockIdx.x < L.nseg) {
@@ -965,7 +1027,7 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     if (TMA && full) {
         __syncthreads();                 // the mbarrier thread 0 initialised is visible to everybody
         mbar_wait(mbar, 0);
-        staged_body<NOISE, PRIOR, NOISE_FIRST, SUMS>(L, keys, dyn, cx, c, sd, seg, sP, sG, sM, acc);
+        staged_body<NOISE, PRIOR, NOISE_FIRST, SUMS>(L, keys, dyn, cx, c, sd, hyper_term, scale_free, sP, sG, sM, acc);
     } else {
         // Nearly every chunk is a full one of a launch that reads all three streams: that case can run
         // without the per-quad bounds / flag tests and without the zero fill (FULL), the rest (the last
@@ -973,9 +1035,9 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
         // (measured per variant, profiles/r02_notes.md: the split pays for the variants that reduce every sum)
         constexpr bool SPLIT = !TMA && (BNNP_FULL_MODE == 1 || (BNNP_FULL_MODE == 2 && SUMS == SUMS_ALL));
         if (SPLIT && full)
-            chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, true>(L, keys, dyn, cx, c, sd, seg, gsrc, acc);
+            chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, true>(L, keys, dyn, cx, c, sd, hyper_term, scale_free, gsrc, acc);
         else
-            chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, false>(L, keys, dyn, cx, c, sd, seg, gsrc, acc);
+            chunk_body<NOISE, PRIOR, NOISE_FIRST, SUMS, false>(L, keys, dyn, cx, c, sd, hyper_term, scale_free, gsrc, acc);
     }
 
     // ---- chunk reduction: fp32 butterfly inside the warp, fp64 across warps (fixed order)
@@ -998,6 +1060,10 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < NWARPS; ++w) s += s_red[w][tid];
+        // BNNP_F_HYPER_POST: a hyper segment stashes the value it leaves in P where the next launch (which
+        // may already be rewriting P) and the epilogue find it (stashed_u); the __syncthreads above made
+        // thread 0's store visible
+        if (PRIOR && tid == R_LOGP && (flags & BNNP_F_HYPER_POST) && is_hyper_kind(sd.prior_kind)) s = (double)L.P[sd.off];
         L.partials[((int64_t)dyn.parity * L.nchunks_total + chunk) * BNNP_NRED + tid] = s;
     }
     if (tid == 0) L.stamps[(int64_t)dyn.parity * L.nchunks_total + chunk] = dyn.call + 1;   // "this launch wrote it"
@@ -1356,9 +1422,14 @@ int bnnp_launch(const BnnpLaunch* a, void* stream) {
     if (misaligned(a->P) || misaligned(a->G) || misaligned(a->M) || misaligned(a->prev_p) || misaligned(a->prev_g) ||
         misaligned(a->prev_m) || misaligned(a->replay_noise) || misaligned(a->chunks))
         return fail(BNNP_E_ALIGN, "bnnp_launch: flat arrays and the chunk table must be 16-byte aligned");
-    if (host_state && a->pending.valid && (a->pending.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)))
+    if (host_state && a->pending.valid && (a->pending.flags & (BNNP_F_HYPER | BNNP_F_HYPER_POST)) &&
+        !((a->pending.flags & BNNP_F_HYPER_POST) && (f & BNNP_F_HYPER_CHAIN)))
         return fail(BNNP_E_ARG, "bnnp_launch: the epilogue of a BNNP_F_HYPER / BNNP_F_HYPER_POST launch rewrites the "
-                                "segment table; bnnp_finalize first");
+                                "segment table; bnnp_finalize first (or, for BNNP_F_HYPER_POST, launch with BNNP_F_HYPER_CHAIN)");
+    if ((f & BNNP_F_HYPER_CHAIN) && host_state && !(a->pending.valid && (a->pending.flags & BNNP_F_HYPER_POST)))
+        return fail(BNNP_E_ARG, "bnnp_launch: BNNP_F_HYPER_CHAIN needs a pending BNNP_F_HYPER_POST epilogue");
+    if ((f & BNNP_F_HYPER_CHAIN) && ((f & BNNP_F_HYPER) || a->chunk_ids != nullptr))
+        return fail(BNNP_E_ARG, "bnnp_launch: BNNP_F_HYPER_CHAIN is for launches over all chunks other than the pre-pass");
     if ((f & BNNP_F_HYPER_POST) &&
         ((f & BNNP_F_HYPER) || a->chunk_ids != nullptr ||
          (f & (BNNP_F_WRITE_P | BNNP_F_PRIOR_GRAD | BNNP_F_LOG_PRIOR)) !=

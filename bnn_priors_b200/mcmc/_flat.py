@@ -494,9 +494,12 @@ class FlatGroup:
         return 0
 
     def after_hyper_post(self) -> None:
-        """The epilogue of a BNNP_F_HYPER_POST step rewrites the segment table: apply it now; then
-        scales, hyper gradients and log-priors describe the parameters the step left in P."""
-        self.flush_pending()
+        """After a BNNP_F_HYPER_POST step, scales, hyper gradients and log-priors describe the
+        parameters the step left in P -- once its epilogue has been applied.  It stays pending: the next
+        launch carries it (BNNP_F_HYPER_CHAIN, see `launch`) or whoever needs the numbers flushes it.
+        (Capturable mode finalises at once: the host cannot tell what a replayed graph left pending.)"""
+        if self.capturable:
+            self.flush_pending()
         self._hyper_valid = self._lp_valid = True
         self._hyper_pversion = self._lp_pversion = self._p_version()
 
@@ -653,6 +656,14 @@ class FlatGroup:
                chunks=None) -> None:
         if chunks is not None:
             self.flush_pending()      # every segment's pending epilogue needs a CTA; a partial launch has none for some
+        pend = self._pending
+        if pend is not None and pend is not True and (pend[3] & N.F_HYPER_POST):
+            # the epilogue of a step with sampled scales rewrites the segment table: it may ride on a launch
+            # over all chunks that derives what it needs from the pending records itself, or is applied first
+            if chunks is None and not (flags & N.F_HYPER) and not self._table_dirty:
+                flags |= N.F_HYPER_CHAIN
+            else:
+                self.flush_pending()
         if self._table_dirty:
             self._upload_table()
         if self._static_dirty:

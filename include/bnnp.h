@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BNNP_ABI_VERSION 9
+#define BNNP_ABI_VERSION 10
 
 #define BNNP_SEG_ALIGN 32      /* floats: every segment starts on a 128-byte line */
 #ifndef BNNP_THREADS
@@ -124,9 +124,19 @@ enum {
                                        BNNP_F_HYPER pre-pass would do for the parameters this
                                        launch leaves in P, because for those two densities the
                                        statistic of d log p / d scale follows from the sum of
-                                       log-density terms the launch reduces anyway (sum d^2 =
-                                       -2 s^2 sum(-z^2/2), sum |d| = -s sum(-|z|)).  Saves the
-                                       pre-pass of the NEXT step.                          */
+                                       log-density terms the launch reduces anyway: for such
+                                       segments the launch reduces sum(-d^2/2) resp. sum(-|d|),
+                                       independent of the scale it used.  Saves the pre-pass of
+                                       the NEXT step; with BNNP_F_HYPER_CHAIN on that next launch
+                                       also the bnnp_finalize in between.                   */
+    BNNP_F_HYPER_CHAIN = 1u << 17,  /* this launch (all chunks, not the pre-pass) carries a PENDING
+                                       BNNP_F_HYPER_POST epilogue instead of having it finalised first:
+                                       a segment with a sampled scale derives its scale, a hyper segment
+                                       its gradient term, from the pending launch's partial records (the
+                                       hyper-parameter that launch left is stashed there), while the CTAs
+                                       that apply the epilogue write the same values into the segment
+                                       table / state for the host.  A step with sampled scales is then ONE
+                                       launch, like any other step                                   */
     BNNP_F_REVERSE = 1u << 15,      /* CTA i processes chunk nchunks-1-i.  A chain larger than
                                        L2 that alternates the direction from launch to launch
                                        starts each launch on the lines the previous one

@@ -59,8 +59,8 @@ def test_kernel_matches_reference_log_prob_and_gradients(case):
     assert fg.hyper_post_ok == post
     launches = fg.launches
     opt.step(calc_metrics=False)
-    # the pre-pass was fresh: one launch (+ the epilogue launch of BNNP_F_HYPER_POST)
-    assert fg.launches == launches + (2 if post else 1)
+    # the pre-pass was fresh: one launch (the epilogue of a BNNP_F_HYPER_POST step stays pending)
+    assert fg.launches == launches + 1
     assert fg.hyper_fresh() == post
     moved = params[1].detach().cpu().numpy().astype(np.float64) - p_ref.astype(np.float64)
     tol = 2e-5 * np.abs(g_ref) + 2.5e-7 * np.maximum(np.abs(p_ref), np.abs(p_ref + g_ref)) + 1e-30
@@ -81,10 +81,14 @@ def test_kernel_matches_reference_log_prob_and_gradients(case):
             for row, col in ((1, N.S_LOG_PRIOR), (2, N.S_LOG_PRIOR), (2, N.S_HYPER), (1, N.S_HYPER)):
                 assert math.isclose(after[row, col], again[row, col], rel_tol=2e-5, abs_tol=1e-6), (row, col, after[row, col], again[row, col])
     # a second step: pre-pass + epilogue + step where the scale statistic needs the new scale (StudentT),
-    # step + epilogue otherwise
+    # the step alone otherwise
     launches = fg.launches
     opt.step(calc_metrics=False)
-    assert fg.launches == launches + (2 if post else 3)
+    assert fg.launches == launches + (1 if post else 3)
+    if post:
+        # ... and a third one carries the second one's pending epilogue (BNNP_F_HYPER_CHAIN): still one launch
+        opt.step(calc_metrics=False)
+        assert fg.launches == launches + 2
 
 
 CASES = [(LM.Normal, "gamma", {}), (LM.Normal, "uniform", {}), (LM.Normal, "horseshoe", dict(hyperscale=2.0)),
@@ -167,6 +171,70 @@ def test_fused_hierarchical_prior_follows_autograd(base, hyper, extra, sampler):
     fp.unfuse()
     assert not fg.has_hyper and not fg.prior_fused
     assert float(mb.log_prior()) == pytest.approx(float(ma.log_prior()), rel=5e-6, abs=1e-4)
+
+
+@pytest.mark.parametrize("sampler", ["VerletSGLD", "SGLD", "HMC"])
+def test_chained_epilogue_gives_the_bits_of_the_finalised_one(sampler):
+    """Steps with sampled scales (Normal / Laplace) chain: the BNNP_F_HYPER_POST epilogue of a step rides on
+    the next launch (BNNP_F_HYPER_CHAIN), whose CTAs derive the new scales and hyper gradients from the pending
+    records themselves.  Same bits as applying every epilogue with bnnp_finalize before the next launch."""
+    from bnn_priors_b200 import _native as N
+    from bnn_priors_b200 import mcmc
+
+    def build():
+        g = torch.Generator(device=DEV).manual_seed(7)
+        shapes = [(300,), (), (5000,), (), (40, 130), (), (17,)]
+        params = [torch.nn.Parameter(torch.randn(s, device=DEV, generator=g) * 0.3 if len(s) else
+                                     torch.tensor(0.2, device=DEV)) for s in shapes]
+        hp = dict(lr=2e-3, num_data=50.0) if sampler == "HMC" else dict(lr=2e-3, num_data=50.0, momentum=0.9, temperature=1.0)
+        if sampler == "HMC":
+            hp["raise_on_nan"] = False
+        opt = getattr(mcmc, sampler)(params, **hp, seed=5)
+        (fg,) = opt.flat_groups
+        fg.set_prior(0, N.PRIOR_NORMAL, 0.0, 1.0, 3.0)
+        fg.set_hyper_link(0, 1, N.PRIOR_HYPER_GAMMA, 1.5, 0.7)
+        fg.set_prior(2, N.PRIOR_LAPLACE, 0.1, 1.0, 3.0)
+        fg.set_hyper_link(2, 3, N.PRIOR_HYPER_IMPROPER, 0.0, 1.0)
+        fg.set_prior(4, N.PRIOR_NORMAL, 0.0, 1.0, 3.0)
+        fg.set_hyper_link(4, 5, N.PRIOR_HYPER_HALFCAUCHY, 1.0, 2.0)
+        fg.set_prior(6, N.PRIOR_STUDENT_T, 0.0, 0.5, 4.0)         # constant hyper-parameters
+        fg.prior_fused = True
+        return opt, params, fg
+
+    oa, pa, fa = build()
+    ob, pb, fb = build()
+    gg = torch.Generator(device=DEV).manual_seed(9)
+    oa.sample_momentum(); ob.sample_momentum()
+    chained = 0
+    bufs = {id(o): [torch.empty_like(p) for p in ps] for o, ps in ((oa, pa), (ob, pb))}    # gradients that stay put
+    for it in range(9):
+        grads = [torch.randn(p.shape, device=DEV, generator=gg) * 0.05 for p in pa]
+        for o, ps in ((oa, pa), (ob, pb)):
+            o.zero_grad()
+            for p, t, buf in zip(ps, grads, bufs[id(o)]):
+                buf.copy_(t)
+                p.grad = buf
+        la = fa.launches
+        if it == 0 and sampler != "SGLD":
+            oa.initial_step(save_state=True, calc_metrics=False); ob.initial_step(save_state=True, calc_metrics=False)
+        else:
+            oa.step(calc_metrics=(it == 4)); ob.step(calc_metrics=(it == 4))
+        if it >= 2:
+            assert fa.launches == la + 1              # one launch per step: nothing is finalised in between
+            chained += 1
+        fb.flush_pending()                            # chain b: every epilogue applied before the next launch
+        if it == 5:
+            oa.sample_momentum(keep=0.5); ob.sample_momentum(keep=0.5)    # a launch without a prior carries it too
+            fb.flush_pending()
+        for p, q in zip(pa, pb):
+            assert torch.equal(p, q), (it, p.shape)
+    assert chained >= 6
+    sa, sb = fa.fetch().copy(), fb.fetch().copy()
+    for col in (N.S_LOG_PRIOR, N.S_HYPER, N.S_SUM_GG, N.S_SQ_MEAN):
+        assert (sa[:, col] == sb[:, col]).all(), col
+    ta = np.frombuffer(fa.table_dev.cpu().numpy().tobytes(), dtype=N.SEGMENT_DTYPE)["prior_scale"]
+    tb = np.frombuffer(fb.table_dev.cpu().numpy().tobytes(), dtype=N.SEGMENT_DTYPE)["prior_scale"]
+    assert (ta == tb).all()
 
 
 def test_lookalikes_are_left_to_autograd():
