@@ -594,8 +594,8 @@ def run_gpu(args):
                            "param_updates_per_s": n / (b2b["kernel_us"] * 1e-6), "alg_GBs": b2b["achieved"]}
 
         # hierarchical priors: every prior-carrying weight tensor gets a sampled scale
-        # (NormalGamma); a step = the step launch + its epilogue launch (BNNP_F_HYPER_POST), timed
-        # through the API
+        # (NormalGamma); a step = ONE launch (BNNP_F_HYPER_POST, its epilogue rides on the next step:
+        # BNNP_F_HYPER_CHAIN), timed through the API
         try:
             from bnn_priors_b200 import mcmc
             del opt, params, fg
@@ -622,7 +622,7 @@ def run_gpu(args):
             for _ in range(5):
                 hstep()
             ms = timed_gpu(hstep, min(K, 50), device, False) / min(K, 50)
-            extra[f"VerletSGLD.step+{len(links)}_sampled_scales(step+epilogue_launch)"] = {
+            extra[f"VerletSGLD.step+{len(links)}_sampled_scales(one launch, chained epilogue)"] = {
                 "us_per_step": ms * 1e3, "param_updates_per_s": n / (ms * 1e-3), "alg_GBs": ALG_BYTES_PER_PARAM * n / (ms * 1e-3) / 1e9}
         except Exception as e:      # context only: never lose the headline because of it
             extra["VerletSGLD.step+sampled_scales"] = {"error": repr(e)}

@@ -3,10 +3,13 @@ around `bnnp_launch` (include/bnnp.h).
 
 The reference keeps one tensor per parameter for p, p.grad, momentum_buffer,
 square_avg, prev_* and loops over them in Python (mcmc/sgld.py:94-105).  Here a
-group owns three (six with snapshots) flat fp32 arrays; the model's parameters,
-their .grad and state['momentum_buffer'] are re-pointed to views of them, so the
-whole group is updated by one kernel launch and the reference's callers
-(runners, lr schedulers, load_state_dict) keep seeing ordinary tensors.
+group owns flat fp32 arrays for the parameters, the momenta and (once asked for)
+the snapshots; the model's parameters and state['momentum_buffer'] are re-pointed
+to views of them, so the whole group is updated by one kernel launch and the
+reference's callers (runners, lr schedulers, load_state_dict) keep seeing ordinary
+tensors.  Gradients are read where autograd leaves them: a small device table holds
+one pointer per tensor (the tensor backward() produced, or the tensor's slice of the
+flat G array) and is rewritten only when an address changes.
 
 torch is used for device memory and streams only.
 """
