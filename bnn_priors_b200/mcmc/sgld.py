@@ -270,6 +270,9 @@ class SGLD(torch.optim.Optimizer):
         """sgld.py:102-104: a non-finite gradient raises BEFORE anything is updated.  One read-only
         launch over the gradients (4 B/param) + the read-back of the per-tensor flags; only with
         `raise_on_nan=True` (HMC's default)."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("raise_on_nan=True reads a flag back from the device at every step and cannot be "
+                               "recorded in a CUDA graph: construct the sampler with raise_on_nan=False")
         fg.launch(N.OP_REDUCE, N.PHASE_MID, N.F_READ_G, N.NOISE_NONE, cm=1.0, chunks=chunks)
         fg._gg_sig = None
         st = fg.fetch()

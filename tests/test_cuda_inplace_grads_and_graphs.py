@@ -262,6 +262,21 @@ def test_a_stale_coefficient_is_not_baked_into_a_graph():
     assert all(torch.isfinite(p).all() for p in params)
 
 
+def test_raise_on_nan_refuses_to_be_captured():
+    opt, params = _make("HMC", capturable=True, raise_on_nan=True)
+    opt.sample_momentum()
+    for p in params:
+        p.grad = torch.randn_like(p)
+    opt.initial_step(save_state=False)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="raise_on_nan=False"):
+        with torch.cuda.graph(torch.cuda.CUDAGraph()):
+            opt.step(calc_metrics=False)
+    torch.cuda.synchronize()
+    opt.step(calc_metrics=False)                 # eager steps are unaffected
+    assert all(torch.isfinite(p).all() for p in params)
+
+
 def test_state_dict_round_trip():
     grads = _grads(SHAPES, 4)
     a, pa = _make("VerletSGLD")
