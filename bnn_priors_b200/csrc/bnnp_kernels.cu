@@ -373,6 +373,16 @@ __device__ __forceinline__ void st_f4_hint(float* p, const float4& v, uint64_t p
 __device__ __forceinline__ float4 ld_grad(const float* p) {
     return BNNP_G_POLICY == 1 ? ld_f4_hint(p, POLICY_EVICT_FIRST) : ld_f4(p);
 }
+// The quad that straddles the end of a tensor: only its valid floats are read.  (P, M and the flat G
+// are padded to whole 128-byte lines, but a gradient tensor autograd handed over ends where it ends.)
+__device__ __forceinline__ float4 ld_grad_tail(const float* p, int valid) {
+    F4 v;
+    v.v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        if (j < valid) v.f[j] = p[j];
+    return v.v;
+}
 __device__ __forceinline__ float4 ld_state(const float* p) {
     return BNNP_PM_POLICY == 2 ? ld_f4_hint(p, POLICY_EVICT_LAST) : ld_f4(p);
 }
@@ -895,11 +905,20 @@ __device__ __forceinline__ void chunk_body(const BnnpLaunch& L, const PhiloxKeys
         } else {
             const bool act = e < cx.rem;
             p[u].v = (act && (flags & BNNP_F_READ_P)) ? ld_state(L.P + cx.fbase + e) : zero4;
-            g[u].v = (act && (flags & BNNP_F_READ_G)) ? ld_grad(gsrc + e) : zero4;
+            // whole quads only: P, M and the flat G are padded to whole 128-byte lines, but a gradient tensor
+            // autograd handed over ends where it ends (the quad that straddles its end is fetched below)
+            g[u].v = (e + 4 <= cx.rem && (flags & BNNP_F_READ_G)) ? ld_grad(gsrc + e) : zero4;
             m[u].v = (act && (flags & BNNP_F_READ_M)) ? ld_state(L.M + cx.fbase + e) : zero4;
             if (NOISE == BNNP_NOISE_REPLAY) z[u].v = act ? ld_f4(L.replay_noise + cx.fbase + e) : zero4;
             else z[u].v = zero4;
         }
+    }
+    if (!FULL && (cx.rem & 3) && (flags & BNNP_F_READ_G)) {
+        // (uniform over the CTA: only the last chunk of a tensor whose size is not a multiple of 4)
+        const int et = cx.rem & ~3;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if ((u * THREADS + tid) * 4 == et) g[u].v = ld_grad_tail(gsrc + et, cx.rem - et);
     }
 
     if (PRIOR) {
