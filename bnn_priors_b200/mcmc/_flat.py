@@ -245,6 +245,7 @@ class FlatGroup:
         self._var_ptrs = None            # (prev_m, replay_noise, chunk_ids) now in self.args
         self.launches = 0
         self.copies = 0                  # gradients that had to be copied into G (not readable in place)
+        self.table_writes = 0            # rewrites of the device table of gradient pointers
 
         self.adopt_parameters()
         self._write_grad_table(list(self._gv_ptrs))
@@ -344,7 +345,7 @@ class FlatGroup:
                 N.check(self.lib.bnnp_poke(base + 8 * lo, part.ctypes.data, part.nbytes, stream), "bnnp_poke")
         self._g_ptrs = list(ptrs)
         self.launches += (self.nseg + 479) // 480
-        self.table_writes = getattr(self, "table_writes", 0) + 1
+        self.table_writes += 1
 
     @torch.no_grad()
     def _readopt_parameters(self) -> None:
