@@ -3,12 +3,35 @@ sampler classes wrapped by tests/runner_tape.py.  Shared by the CPU self-check o
 and the GPU parity tests.  Test infrastructure only."""
 from __future__ import annotations
 
+import contextlib
 import importlib
 
 import torch
 
 import refenv
 import runner_tape as RT
+
+@contextlib.contextmanager
+def deterministic_generators(base_seed: int = 20240):
+    """The Reject runners seed the minibatch order from OS entropy (`generator.seed()`,
+    inference_reject.py:68-72), so every run sees another trajectory.  For reproducible tests every
+    `torch.Generator()` created while this context is active answers `seed()` with a counter-based
+    value instead (test-side; the reference's code is untouched)."""
+    real = torch.Generator
+    counter = {"n": 0}
+
+    class CountingSeedGenerator(real):
+        def seed(self):
+            counter["n"] += 1
+            s = base_seed + counter["n"]
+            self.manual_seed(s)
+            return s
+    torch.Generator = CountingSeedGenerator
+    try:
+        yield
+    finally:
+        torch.Generator = real
+
 
 RUNNERS = {
     "SGLD": ("bnn_priors.inference", "SGLDRunner"),
@@ -65,7 +88,7 @@ def record_run(inference, config, device, seed=0, with_prior_grads=False, **kw):
     torch.manual_seed(seed)
     runner, model, _ = make_runner(inference, config, device, seed=seed, **kw)
     pg = prior_grad_fn_for(model, lambda: runner.eff_num_data) if with_prior_grads else None
-    with RT.bound_sampler_classes(ref_mcmc, lambda c: RT.recording_class(c, tape, pg)):
+    with RT.bound_sampler_classes(ref_mcmc, lambda c: RT.recording_class(c, tape, pg)), deterministic_generators():
         runner.run(progressbar=False)
     return tape, runner
 
@@ -81,7 +104,8 @@ def replay_run(inference, config, device, tape, seed=0, fused_prior=False, befor
     runner, model, _ = make_runner(inference, config, device, seed=seed, **kw)
     if before_run is not None:
         before_run(runner, model)
-    with RT.bound_sampler_classes(ref_mcmc, lambda c: RT.replaying_class(c, tape, report, fused_prior)):
+    with RT.bound_sampler_classes(ref_mcmc, lambda c: RT.replaying_class(c, tape, report, fused_prior)), \
+            deterministic_generators():
         runner.run(progressbar=False)
     assert tape.cursor == len(tape.events), "the replayed run made fewer sampler calls than the recorded one"
     return report, runner
@@ -90,7 +114,6 @@ def replay_run(inference, config, device, tape, seed=0, fused_prior=False, befor
 def run_train_bnn(log_dir, device="try_cuda", n_train=512, n_test=256, **config_updates):
     """experiments/train_bnn.py's `main` (train_bnn.py:155-259), unmodified, through the sacred / h5py
     test shims, on synthetic data of the named data set's shape.  Returns (run, run directory)."""
-    import contextlib
     mod = refenv.load_train_bnn()
     eu = refenv.exp_utils()
     real_get_data = eu.get_data
@@ -115,7 +138,7 @@ def run_train_bnn(log_dir, device="try_cuda", n_train=512, n_test=256, **config_
             super().__init__(module, device_ids=[p.device.index or 0], output_device=output_device, dim=dim)
     eu.t.nn.DataParallel = OneDeviceDataParallel
     try:
-        with contextlib.redirect_stdout(None):
+        with contextlib.redirect_stdout(None), deterministic_generators():
             run = mod.ex.run(config_updates=cfg)
     finally:
         eu.get_data = real_get_data
