@@ -40,6 +40,8 @@ CASES = {
     "cfg1_densenet_sgld_gaussian": ("SGLD", "densenet_gaussian", dict(n_train=1024, lr=5e-4)),
     "densenet_verlet_noreject": ("VerletSGLD", "densenet_gaussian", dict(n_train=1024, lr=1e-2)),
     "googleresnet_sgld_reject_runner": ("SGLDReject", "googleresnet_studentt", dict(n_train=512, lr=5e-4)),
+    # inference.py:368-374 (HMCRunner: the non-"Reject" HMC loop, momentum re-sampled at every sampling epoch)
+    "convnet_hmc_runner_laplace": ("OurHMC", "convnet_laplace", dict(n_train=1024, lr=2e-3)),
 }
 
 
