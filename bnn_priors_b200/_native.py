@@ -190,6 +190,32 @@ def lib() -> C.CDLL:
     return l
 
 
+_host = False
+
+
+def host_module():
+    """The optional host-side helper (csrc/bnnp_host.cpp, built by `bnn_priors_b200.build.build_host`) or None.
+    BNNP_HOST_SCAN=0 disables it (the Python scan in mcmc/_flat.py is the specification and the fallback)."""
+    global _host
+    if _host is not False:
+        return _host
+    _host = None
+    path = os.path.join(HERE, "_lib", "_host", "bnnp_host.so")
+    if os.environ.get("BNNP_HOST_SCAN", "1") != "0" and os.path.exists(path):
+        try:
+            import importlib.machinery
+            import importlib.util
+            import torch  # noqa: F401  (the extension links against libtorch)
+            loader = importlib.machinery.ExtensionFileLoader("bnnp_host", path)
+            spec = importlib.util.spec_from_loader("bnnp_host", loader)
+            mod = importlib.util.module_from_spec(spec)
+            loader.exec_module(mod)
+            _host = mod
+        except Exception:           # another torch / python than it was built for: Python scan
+            _host = None
+    return _host
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise BnnpError(f"{what} failed ({rc}): {lib().bnnp_last_error().decode()}")

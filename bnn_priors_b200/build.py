@@ -72,5 +72,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+HOST_SRC = os.path.join(HERE, "csrc", "bnnp_host.cpp")
+HOST_DIR = os.path.join(HERE, "_lib", "_host")
+HOST_OUT = os.path.join(HOST_DIR, "bnnp_host.so")
+
+
+def build_host(force: bool = False, verbose: bool = False) -> str:
+    """Compile the optional host-side helper (csrc/bnnp_host.cpp: the per-step scan of the parameters'
+    gradients over the ATen objects instead of Python attribute calls) as a torch C++ extension, in-tree.
+    CPU code only; the samplers run without it (Python scan)."""
+    if not force and os.path.exists(HOST_OUT) and os.path.getmtime(HOST_OUT) >= os.path.getmtime(HOST_SRC):
+        return HOST_OUT
+    from torch.utils import cpp_extension
+    os.makedirs(HOST_DIR, exist_ok=True)
+    cpp_extension.load(name="bnnp_host", sources=[HOST_SRC], build_directory=HOST_DIR, extra_cflags=["-O2"],
+                       verbose=verbose)
+    if not os.path.exists(HOST_OUT):
+        raise RuntimeError("building the host helper left no bnnp_host.so")
+    return HOST_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    try:
+        print(build_host(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    except Exception as e:          # optional: the samplers fall back to the Python scan
+        print("host helper not built:", e, file=sys.stderr)

@@ -248,6 +248,9 @@ class FlatGroup:
         self.table_writes = 0            # rewrites of the device table of gradient pointers
 
         self.adopt_parameters()
+        hm = N.host_module()
+        # optional C++ helper for the per-step scan below (csrc/bnnp_host.cpp); None: the Python scan
+        self._scanner = hm.GradScanner(self.params, self._p_ptrs) if hm is not None else None
         self._write_grad_table(list(self._gv_ptrs))
 
     # ------------------------------------------------------------------ views
@@ -270,6 +273,14 @@ class FlatGroup:
         hands back the same blocks, so: never).  A parameter whose storage was swapped
         (`Prior.sample()`) is re-adopted.  Returns the indices of parameters that have no gradient
         (sgld.py:96-101)."""
+        sc = self._scanner
+        if sc is not None:
+            # the same scan over the ATen objects: 0 = every gradient lies where the device table says and
+            # every parameter is still its flat view (the steady state of a training loop)
+            rc = sc.scan()
+            if rc == 0:
+                self._held_grads = None
+                return _NO_MISSING
         grads = list(map(_GRAD, self.params))
         try:
             ptrs = list(map(_DATA_PTR, grads))
@@ -344,6 +355,8 @@ class FlatGroup:
                 part = np.ascontiguousarray(arr[lo:lo + 480])
                 N.check(self.lib.bnnp_poke(base + 8 * lo, part.ctypes.data, part.nbytes, stream), "bnnp_poke")
         self._g_ptrs = list(ptrs)
+        if self._scanner is not None:
+            self._scanner.set_table(self._g_ptrs)
         self.launches += (self.nseg + 479) // 480
         self.table_writes += 1
 
@@ -362,17 +375,24 @@ class FlatGroup:
                 p.grad = v
         self._g_seen = [None] * self.nseg
         self._held_grads = None
+        if self._scanner is not None:
+            self._scanner.drop()
 
     def drop_grads(self) -> None:
         "zero_grad(set_to_none=True): p.grad = None (a fused hyper-parameter keeps its zero view)"
-        for p in self.params:
-            p.grad = None
-        for i in self.hyper_links:
-            if self.prior_fused:
+        keep = sorted(self.hyper_links) if (self.prior_fused and self.hyper_links) else []
+        if self._scanner is not None and all(self.params[i].grad is self.g_views[i] and self._g_seen[i] == "zero" for i in keep):
+            self._scanner.drop_grads(keep)
+        else:
+            for p in self.params:
+                p.grad = None
+            for i in keep:
                 if self._g_seen[i] != "zero":
                     self.g_views[i].zero_()
                     self._g_seen[i] = "zero"
                 self.params[i].grad = self.g_views[i]
+            if self._scanner is not None:
+                self._scanner.drop()
         self._held_grads = None
         self._gg_sig = None
 
@@ -729,6 +749,8 @@ class FlatGroup:
 
     # ------------------------------------------------------------ reductions on demand
     def _p_version(self) -> int:
+        if self._scanner is not None:
+            return self._scanner.params_version()
         return sum(p._version for p in self.params)
 
     def note_step_sums(self, flags: int, op: int, capture_grads: bool = True) -> None:
@@ -737,7 +759,9 @@ class FlatGroup:
         describes M as stored if the launch reduced every sum; LOG_PRIOR describes P as stored if
         it carried BNNP_F_LOG_PRIOR."""
         held = self._held_grads
-        if capture_grads and held is not None:
+        if capture_grads and self._scanner is not None:
+            self._gg_sig = "scanner" if self._scanner.capture() else None
+        elif capture_grads and held is not None:
             try:
                 self._gg_sig = (held, list(map(_VERSION, held)))
             except AttributeError:             # a parameter without gradient was skipped
@@ -756,6 +780,8 @@ class FlatGroup:
 
     def invalidate_sums(self) -> None:
         self._gg_sig = self._mm_version = None
+        if self._scanner is not None:
+            self._scanner.drop()
         self._lp_valid = self._hyper_valid = False
 
     def reduce_now(self, inv_num_data: float) -> None:
@@ -791,6 +817,10 @@ class FlatGroup:
         sig = self._gg_sig
         if sig is None:
             return False
+        if sig == "scanner":
+            if not self._scanner.fresh():
+                return False
+            return not (need_mm and (self.M is None or self._mm_version != self.M._version))
         cur = list(map(_GRAD, self.params))
         if len(cur) != len(sig[0]) or not all(map(_IS, cur, sig[0])) or list(map(_VERSION, cur)) != sig[1]:
             return False
