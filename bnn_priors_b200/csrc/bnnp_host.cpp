@@ -33,7 +33,11 @@ struct GradScanner {
         const size_t n = params.size();
         for (size_t i = 0; i < n; ++i) {
             const at::Tensor& g = params[i].grad();
-            if (!g.defined() || reinterpret_cast<int64_t>(g.data_ptr()) != table[i]) return 1;
+            // (layout and type again, not only the address: a transposed view of a square gradient starts at the
+            //  same byte -- the Python slow path then copies it)
+            if (!g.defined() || reinterpret_cast<int64_t>(g.data_ptr()) != table[i] || !g.is_contiguous() ||
+                g.scalar_type() != at::kFloat)
+                return 1;
         }
         for (size_t i = 0; i < n; ++i)
             if (reinterpret_cast<int64_t>(params[i].data_ptr()) != p_ptrs[i]) return 2;

@@ -33,6 +33,13 @@ def test_scan_answers(hm):
     assert sc.scan() == 1
     ps[1].grad = keep[1]
     assert sc.scan() == 0
+    sq = torch.nn.Parameter(torch.randn(4, 4))
+    sq.grad = torch.randn(4, 4)
+    sc2 = hm.GradScanner([sq], [sq.data_ptr()])
+    sc2.set_table([sq.grad.data_ptr()])
+    assert sc2.scan() == 0
+    sq.grad = sq.grad.t()                                  # same first byte, another layout
+    assert sc2.scan() == 1
     ps[2].data = torch.tensor(1.0)                         # a parameter's storage was swapped
     assert sc.scan() == 2
     ps[3].grad = None
