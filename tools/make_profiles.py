@@ -131,7 +131,7 @@ def notes_md(out, have_multi):
             L.append(f"| {n} | {d['value']:.4g} | {d['ms_per_step']*1e3 - d['roofline']['kernel_us']:+.2f} | {d['value']/(n*v1):.3f} | {d['samplers']['VerletSGLD.step']['value']:.4g} | "
                      f"{d['samplers']['HMC.step']['value']:.4g} | {d['e2e']['value']:.4g} | {d['e2e']['bare_h2d_GBs_per_gpu']:.1f} | {d.get('cycle_gather_ms') and round(d['cycle_gather_ms'], 3)} |")
         L.append("\n`smoke()` on the 2-GPU and on the 8-GPU box: `N chains on N GPUs, NCCL gather == independent runs (bit for bit)`; "
-                 "`tests/test_cuda_chains_nccl.py` passed on both. (Measured before the TMA staging / chained epilogue went in; the plain SGLD / Verlet / HMC step kernels these lines time did not change.)\n")
+                 "`tests/test_cuda_chains_nccl.py` passed on both (final code of the round).\n")
     L += [f"## Small BASELINE configs (`{out}_small_models.json`: `python tools/bench_small_models.py`), µs per step\n",
           "| config | tensors | host, views | host, runner loop (`zero_grad` / `step`) | kernel | graph replay host / wall | round-1 host |\n|---|---|---|---|---|---|---|"]
     r1 = json.load(open(os.path.join(P, "r01g_small_models.json")))
