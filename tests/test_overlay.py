@@ -42,6 +42,30 @@ def test_overlay_rebinds_the_reference_samplers():
         finally:
             overlay.uninstall()
         assert exp_utils.evaluate_model is ref_eval and inference.evaluate_model is ref_eval
+        # fuse_prior / sample_sink: the runner methods and the sample saver are re-bound, and restored
+        from bnn_priors_b200.sample_sink import FlatSampleSaver
+        make_opt = inference.SGLDRunner.__dict__["_make_optimizer"]
+        make_opt_reject = inference_reject.VerletSGLDRunnerReject.__dict__["_make_optimizer"]
+        pot = inference.SGLDRunner.__dict__["_model_potential_and_grad"]
+        exact = inference_reject.VerletSGLDRunnerReject.__dict__["_exact_model_potential_and_grad"]
+        saver = exp_utils.HDF5ModelSaver
+        overlay.install(fuse_prior=True, sample_sink=True)
+        try:
+            assert inference.SGLDRunner.__dict__["_make_optimizer"] is not make_opt
+            assert inference_reject.VerletSGLDRunnerReject.__dict__["_make_optimizer"] is not make_opt_reject
+            assert inference_reject.HMCRunnerReject.__dict__["_make_optimizer"].__name__ == "_make_optimizer"
+            assert inference.SGLDRunner.__dict__["_model_potential_and_grad"] is not pot
+            assert inference_reject.VerletSGLDRunnerReject.__dict__["_exact_model_potential_and_grad"] is not exact
+            assert exp_utils.HDF5ModelSaver is FlatSampleSaver
+            assert issubclass(exp_utils.HDF5Metrics, saver)          # the metrics writer keeps the reference's base class
+            overlay.install(fuse_prior=True, sample_sink=True)       # idempotent
+        finally:
+            overlay.uninstall()
+        assert inference.SGLDRunner.__dict__["_make_optimizer"] is make_opt
+        assert inference_reject.VerletSGLDRunnerReject.__dict__["_make_optimizer"] is make_opt_reject
+        assert inference.SGLDRunner.__dict__["_model_potential_and_grad"] is pot
+        assert inference_reject.VerletSGLDRunnerReject.__dict__["_exact_model_potential_and_grad"] is exact
+        assert exp_utils.HDF5ModelSaver is saver and ref_mcmc.VerletSGLD is original
     finally:
         sys.path.remove(REFERENCE)
         sys.path.remove(os.path.join(HERE, "golden", "_shims"))
