@@ -1224,20 +1224,34 @@ __global__ void bnnp_poke_kernel(uint32_t* dst, const __grid_constant__ PokePayl
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src.w[i];
 }
 
-// P,G,M <- prev_* : verlet_sgld.py:63-69
+// P,G,M <- prev_* : verlet_sgld.py:63-69.  Three streams copied (24 B/param); UNROLL quads of every stream are
+// loaded before the first store, like the step kernel's front-batched loads.
 __global__ void __launch_bounds__(THREADS) bnnp_rollback_kernel(float* __restrict__ P, float* __restrict__ G,
                                                                 float* __restrict__ M,
                                                                 const float* __restrict__ pp,
                                                                 const float* __restrict__ pg,
                                                                 const float* __restrict__ pm, int64_t nquads) {
-    const int64_t stride = (int64_t)gridDim.x * THREADS;
-    for (int64_t q = (int64_t)blockIdx.x * THREADS + threadIdx.x; q < nquads; q += stride) {
-        const float4 a = ld_f4(pp + 4 * q), b = ld_f4(pg + 4 * q);
-        float4 cc;
-        if (pm != nullptr) cc = ld_f4(pm + 4 * q);
-        st_f4(P + 4 * q, a);
-        st_f4(G + 4 * q, b);
-        if (pm != nullptr) st_f4(M + 4 * q, cc);
+    const int64_t stride = (int64_t)gridDim.x * THREADS * UNROLL;
+    for (int64_t q0 = (int64_t)blockIdx.x * THREADS * UNROLL + threadIdx.x; q0 < nquads; q0 += stride) {
+        float4 a[UNROLL], b[UNROLL], cc[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t q = q0 + (int64_t)u * THREADS;
+            if (q < nquads) {
+                a[u] = ld_f4(pp + 4 * q);
+                b[u] = ld_f4(pg + 4 * q);
+                if (pm != nullptr) cc[u] = ld_f4(pm + 4 * q);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t q = q0 + (int64_t)u * THREADS;
+            if (q < nquads) {
+                st_f4(P + 4 * q, a[u]);
+                st_f4(G + 4 * q, b[u]);
+                if (pm != nullptr) st_f4(M + 4 * q, cc[u]);
+            }
+        }
     }
 }
 
