@@ -175,6 +175,9 @@ def notes_md(out, have_multi):
              f"* `{out}_ncu_variants.json` — the same `--set full` numbers for VerletSGLD + fused prior and the all-sums variant (both TMA-staged), HMC, `initial_step(save_state)`.\n"
              f"* `{out}_ncu_launches.json` — launch list of `bench.py --steps 3 --warmup 3 --no-cpu --no-extra` (first 600 launches).\n"
              f"* `{out}_ncu_foreign_grads.json` — launch list of the reference runner's loop with gradients in tensors of their own: the step kernel only, no copy kernel.\n")
+    add = os.path.join(P, f"{out}_addenda.md")
+    if os.path.exists(add):
+        L.append(open(add).read())
     open(os.path.join(P, f"{out}_notes.md"), "w").write("\n".join(L) + "\n")
 
 
