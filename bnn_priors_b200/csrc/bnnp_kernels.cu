@@ -774,8 +774,23 @@ __device__ __forceinline__ void process_chunk(const BnnpLaunch& L, const ChunkCt
 #ifndef BNNP_TMA_MODE
 #define BNNP_TMA_MODE 2     // 0: never; 1: every variant without a replay buffer; 2: fused-prior and all-sums variants
 #endif
+// What the threads can do without the data happens before they wait for it: the per-segment constants
+// (make_prior: float64 divisions) and, BNNP_TMA_NOISE_AHEAD, the Philox + Box-Muller noise of that many of
+// the thread's quads -- most of the arithmetic of a noisy step, now under the shadow of the bulk copies
+// (profiles/r02z_tma_overlap.jsonl: Verlet + fused prior 72.1 -> 70.4 us back to back, + metrics 77.0 -> 73.8).
+// BNNP_TMA_SUBTILES > 1 lets the chunk arrive as that many consecutive parts of every stream, each on an
+// mbarrier of its own; measured slower (2: +0.5 us, 4: +1 .. +3 us), kept as an option at 1.
+#ifndef BNNP_TMA_SUBTILES
+#define BNNP_TMA_SUBTILES 1
+#endif
+#ifndef BNNP_TMA_NOISE_AHEAD
+#define BNNP_TMA_NOISE_AHEAD 4
+#endif
+constexpr int TMA_SUBTILES = BNNP_TMA_SUBTILES;
+static_assert(TMA_SUBTILES >= 1 && UNROLL % TMA_SUBTILES == 0, "sub-tiles are whole passes of the CTA over the chunk");
 constexpr int TMA_STREAM_BYTES = CHUNK * 4;
-constexpr int TMA_SMEM_BYTES = 3 * TMA_STREAM_BYTES + 16;       // three staged streams + the mbarrier
+constexpr int TMA_SUB_BYTES = TMA_STREAM_BYTES / TMA_SUBTILES;
+constexpr int TMA_SMEM_BYTES = 3 * TMA_STREAM_BYTES + 8 * (TMA_SUBTILES < 2 ? 2 : TMA_SUBTILES);   // three staged streams + the mbarriers
 
 template <int NOISE, bool PRIOR, int SUMS>
 __host__ __device__ constexpr bool use_tma() {
@@ -819,9 +834,23 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uin
 template <int NOISE, bool PRIOR, int KIND, bool NOISE_FIRST, int SUMS>
 __device__ __forceinline__ void process_staged(const BnnpLaunch& L, const ChunkCtx& cx, const Coef& c, const PriorConst& pc,
                                                const PhiloxKeys& keys, const float* sP, const float* sG, const float* sM,
-                                               float acc[BNNP_NRED], const uint32_t flags, const uint64_t call) {
+                                               const uint32_t mbar, float acc[BNNP_NRED], const uint32_t flags,
+                                               const uint64_t call) {
+    // The noise of the first BNNP_TMA_NOISE_AHEAD quads does not need the data: it is generated while the
+    // bulk copies are in flight, which is most of the arithmetic of those quads.
+    constexpr int AHEAD = (NOISE == BNNP_NOISE_PHILOX) ? (BNNP_TMA_NOISE_AHEAD < UNROLL ? BNNP_TMA_NOISE_AHEAD : UNROLL) : 0;
+    F4 za[AHEAD > 0 ? AHEAD : 1];
+#pragma unroll
+    for (int u = 0; u < AHEAD; ++u)
+        philox_normal4((uint64_t)(cx.fbase + (u * THREADS + cx.tid) * 4) >> 2, call, keys, za[u].f);
+#pragma unroll
+    for (int u = 0; u < AHEAD; ++u)      // pin the values in front of the wait (volatile asm statements keep their order)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) asm volatile("" : "+f"(za[u].f[j]));
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
+        constexpr int PER_SUB = UNROLL / TMA_SUBTILES;
+        if (u % PER_SUB == 0) mbar_wait(mbar + 8 * (u / PER_SUB), 0);     // this pass's sub-tile has landed
         const int e = (u * THREADS + cx.tid) * 4;
         const int64_t fi = cx.fbase + e;
         F4 p, g, m, z;
@@ -834,7 +863,8 @@ __device__ __forceinline__ void process_staged(const BnnpLaunch& L, const ChunkC
             st_f4_hint(L.prev_g + fi, g.v, POLICY_EVICT_FIRST);
             if (L.prev_m != nullptr) st_f4_hint(L.prev_m + fi, m.v, POLICY_EVICT_FIRST);
         }
-        if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)fi >> 2, call, keys, z.f);
+        if (u < AHEAD) z.v = za[u < AHEAD ? u : 0].v;
+        else if (NOISE == BNNP_NOISE_PHILOX) philox_normal4((uint64_t)fi >> 2, call, keys, z.f);
         update_quad<NOISE, PRIOR, KIND, NOISE_FIRST, SUMS, true>(flags, c, pc, 4, p, g, m, z.f, acc);
         if (flags & BNNP_F_WRITE_P) st_state(L.P + fi, p.v);
         if (flags & BNNP_F_WRITE_M) st_state(L.M + fi, m.v);
@@ -844,13 +874,14 @@ __device__ __forceinline__ void process_staged(const BnnpLaunch& L, const ChunkC
 template <int NOISE, bool PRIOR, bool NOISE_FIRST, int SUMS>
 __device__ __forceinline__ void staged_body(const BnnpLaunch& L, const PhiloxKeys& keys, const Dyn& dyn, const ChunkCtx& cx,
                                             const Coef& c, const BnnpSegment& sd, float hyper_term, bool scale_free,
-                                            const float* sP, const float* sG, const float* sM, float acc[BNNP_NRED]) {
+                                            const float* sP, const float* sG, const float* sM, const uint32_t mbar,
+                                            float acc[BNNP_NRED]) {
     const uint32_t flags = dyn.flags;
     if (PRIOR) {
 #define BNNP_FORM_CASE(F)                                                                                       \
     case F:                                                                                                     \
         process_staged<NOISE, true, F, NOISE_FIRST, SUMS>(L, cx, c, make_prior<F>(sd, dyn.inv_n, hyper_term, scale_free), \
-                                                          keys, sP, sG, sM, acc, flags, dyn.call);              \
+                                                          keys, sP, sG, sM, mbar, acc, flags, dyn.call);        \
         break;
         switch (prior_form(sd.prior_kind)) {
             BNNP_FORM_CASE(F_NORMAL)
@@ -866,7 +897,8 @@ __device__ __forceinline__ void staged_body(const BnnpLaunch& L, const PhiloxKey
         }
 #undef BNNP_FORM_CASE
     } else {
-        process_staged<NOISE, false, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, PriorConst(), keys, sP, sG, sM, acc, flags, dyn.call);
+        process_staged<NOISE, false, F_NONE, NOISE_FIRST, SUMS>(L, cx, c, PriorConst(), keys, sP, sG, sM, mbar, acc, flags,
+                                                                dyn.call);
     }
 }
 
@@ -967,17 +999,20 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     float* const sG = sP + CHUNK;
     float* const sM = sG + CHUNK;
     const uint32_t mbar = smem_u32(sM + CHUNK);
-    if (TMA && full && tid == 0) {
+    // thread t fetches sub-tile t (floats [t, t+1) * CHUNK / TMA_SUBTILES of every stream) onto mbarrier t
+    const bool fetcher = TMA && full && tid < TMA_SUBTILES;
+    constexpr int SUB = CHUNK / TMA_SUBTILES;
+    if (fetcher) {
         // P and M do not wait for the segment descriptor: their bulk copies go out first
-        mbar_init(mbar, 1);
-        mbar_arrive_expect_tx(mbar, 3 * TMA_STREAM_BYTES);
-        bulk_g2s_hint(smem_u32(sP), L.P + cd.fbase, TMA_STREAM_BYTES, mbar, POLICY_EVICT_LAST);
-        bulk_g2s_hint(smem_u32(sM), L.M + cd.fbase, TMA_STREAM_BYTES, mbar, POLICY_EVICT_LAST);
+        mbar_init(mbar + 8 * tid, 1);
+        mbar_arrive_expect_tx(mbar + 8 * tid, 3 * TMA_SUB_BYTES);
+        bulk_g2s_hint(smem_u32(sP + tid * SUB), L.P + cd.fbase + tid * SUB, TMA_SUB_BYTES, mbar + 8 * tid, POLICY_EVICT_LAST);
+        bulk_g2s_hint(smem_u32(sM + tid * SUB), L.M + cd.fbase + tid * SUB, TMA_SUB_BYTES, mbar + 8 * tid, POLICY_EVICT_LAST);
     }
     BnnpSegment sd = L.segs[seg];
     // the segment's gradient: its slice of the flat G, or the tensor autograd handed over
     const float* gsrc = L.seg_grad != nullptr ? L.seg_grad[seg] + (cd.fbase - sd.off) : L.G + cd.fbase;
-    if (TMA && full && tid == 0) bulk_g2s(smem_u32(sG), gsrc, TMA_STREAM_BYTES, mbar);
+    if (fetcher) bulk_g2s(smem_u32(sG + tid * SUB), gsrc + tid * SUB, TMA_SUB_BYTES, mbar + 8 * tid);
 
     // Sampled scales (hierarchical priors).  Normally the table holds the current scale of a linked segment
     // and the segment state the hyper-parameter's gradient term (left by the epilogue of a pre-pass or of
@@ -1044,9 +1079,8 @@ __global__ void __launch_bounds__(THREADS, min_ctas<NOISE, SUMS, PRIOR>()) bnnp_
     for (int k = 0; k < BNNP_NRED; ++k) acc[k] = 0.0f;
 
     if (TMA && full) {
-        __syncthreads();                 // the mbarrier thread 0 initialised is visible to everybody
-        mbar_wait(mbar, 0);
-        staged_body<NOISE, PRIOR, NOISE_FIRST, SUMS>(L, keys, dyn, cx, c, sd, hyper_term, scale_free, sP, sG, sM, acc);
+        __syncthreads();                 // the mbarriers the fetching threads initialised are visible to everybody
+        staged_body<NOISE, PRIOR, NOISE_FIRST, SUMS>(L, keys, dyn, cx, c, sd, hyper_term, scale_free, sP, sG, sM, mbar, acc);
     } else {
         // Nearly every chunk is a full one of a launch that reads all three streams: that case can run
         // without the per-quad bounds / flag tests and without the zero fill (FULL), the rest (the last

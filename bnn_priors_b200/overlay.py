@@ -149,7 +149,8 @@ def install(reference_package: str = "bnn_priors", evaluate: bool = False, fuse_
     for sub, names in (("sgld", ("SGLD",)), ("verlet_sgld", ("VerletSGLD",)), ("hmc", ("HMC",))):
         m = sys.modules.get(f"{reference_package}.mcmc.{sub}")
         if m is not None:
-            _saved.setdefault("sub", {})[sub] = {n: getattr(m, n) for n in names}
+            # (a repeated install() must not record the classes it put there itself as the originals)
+            _saved.setdefault("sub", {}).setdefault(sub, {n: getattr(m, n) for n in names})
             for n in names:
                 setattr(m, n, getattr(fast, n))
     if evaluate:

@@ -66,6 +66,10 @@ def test_overlay_rebinds_the_reference_samplers():
         assert inference.SGLDRunner.__dict__["_model_potential_and_grad"] is pot
         assert inference_reject.VerletSGLDRunnerReject.__dict__["_exact_model_potential_and_grad"] is exact
         assert exp_utils.HDF5ModelSaver is saver and ref_mcmc.VerletSGLD is original
+        # the submodule bindings too: the reference's own `super(SGLD, self)` (mcmc/sgld.py:39) resolves them
+        from bnn_priors.mcmc import sgld as ref_sgld, verlet_sgld as ref_verlet, hmc as ref_hmc
+        assert ref_sgld.SGLD is not fast.SGLD and issubclass(original, ref_sgld.SGLD)
+        assert ref_verlet.VerletSGLD is original and ref_hmc.HMC is not fast.HMC
     finally:
         sys.path.remove(REFERENCE)
         sys.path.remove(os.path.join(HERE, "golden", "_shims"))
