@@ -162,6 +162,7 @@ class Report:
         self.log_accept_err = 0.0
         self.n_events = 0
         self.ops = {}
+        self.kink_guards = 0         # elements put back on the reference's side of a prior's kink (fused replays)
 
     def bump(self, key, v):
         self.scalar_err[key] = max(self.scalar_err.get(key, 0.0), v)
@@ -203,6 +204,22 @@ def replaying_class(base, tape: Tape, report: Report, fused_prior: bool = False)
             report.ops[op] = report.ops.get(op, 0) + 1
             if "pg_abs" in ev and ev["kwargs"].get("calc_metrics", True):
                 self._last_pg_abs = ev["pg_abs"]     # the step that (re)computes est_config_temp
+            if op in STEP_OPS and fused_prior and tape.cursor >= 2:
+                # A fused replay gets the likelihood gradient and computes the prior's term from ITS parameters.
+                # A Laplace prior's term is sign(p - loc) / (N scale) (prior/loc_scale.py:66-67): discontinuous at
+                # the kink, so an element that lies within the comparison tolerance of the kink on the other side
+                # than the reference's (both are right to 1e-7) would get the opposite term and leave the
+                # reference trajectory for good -- a property of the prior, not of the sampler.  Such elements
+                # (loc = 0 in every prior `get_prior` builds; expected: none to a few per run) are put on the
+                # reference's value before the step; the move is far below TOL and counted in the report.
+                for p, q in zip(params, tape.events[tape.cursor - 2]["after"]["p"]):
+                    q = q.to(p.device)
+                    flip = (torch.sign(p.detach()) != torch.sign(q)) & ((p.detach() - q).abs() <= 1e-5 * q.abs().max())
+                    n_flip = int(flip.sum())
+                    if n_flip:
+                        with torch.no_grad():
+                            p[flip] = q[flip]
+                        report.kink_guards += n_flip
             if op in STEP_OPS:
                 for i, (p, g) in enumerate(zip(params, ev["grads"])):
                     if g is None:

@@ -18,8 +18,10 @@ TUNE = os.path.join(os.path.dirname(B.OUT), "tune")
 
 
 def one(spec: str) -> str:
-    name, _, defs = spec.partition(":")
+    name, _, rest = spec.partition(":")
+    defs, _, src = rest.partition(":")        # an optional third field: another copy of bnnp_kernels.cu (e.g. an older revision)
     defs = [d for d in defs.split(",") if d]
+    src = src or B.SRC[0]
     objdir = os.path.join(TUNE, "_obj_" + name)
     os.makedirs(objdir, exist_ok=True)
     nvcc = B.find_nvcc()
@@ -27,7 +29,7 @@ def one(spec: str) -> str:
     cmds, objs = [], []
     for part in (0, 1, 2):
         objs.append(os.path.join(objdir, f"k{part}.o"))
-        cmds.append([nvcc] + flags + [f"-DBNNP_PART={part}", "-c", B.SRC[0], "-o", objs[-1]])
+        cmds.append([nvcc] + flags + [f"-DBNNP_PART={part}", "-c", src, "-o", objs[-1]])
     objs.append(os.path.join(objdir, "eval.o"))
     cmds.append([nvcc] + flags + ["-c", B.SRC[1], "-o", objs[-1]])
     procs = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in cmds]
