@@ -59,15 +59,17 @@ def parity_md(tag, out):
           "## Under the reference's own runners (`tests/test_cuda_reference_runners.py`)", "",
           "Run A = reference runner + reference eager sampler on cuda:0 (recorded); run B = same runner after `overlay.install()` "
           "(the kernel), every sampler call fed run A's inputs and compared with run A's outputs. Errors: worst over all calls; "
-          "`p`/`m` relative to the tensor's RMS; ΔE against the size of its terms; decisions = Metropolis tests (equal / total, rejections).", "",
-          "| case | sampler calls | p | m | est_temperature | est_config_temp | ΔE (terms) | max abs ΔE | decisions equal | rejections |",
-          "|---|---|---|---|---|---|---|---|---|---|"]
+          "`p`/`m` relative to the tensor's RMS; ΔE against the size of its terms; decisions = Metropolis tests (equal / total, rejections); "
+          "kink = elements a fused replay found within 1e-5 of the reference's value but on the other side of zero, put on the reference's "
+          "value before the step (a Laplace prior's gradient term jumps there; tests/runner_tape.py).", "",
+          "| case | sampler calls | p | m | est_temperature | est_config_temp | ΔE (terms) | max abs ΔE | decisions equal | rejections | kink |",
+          "|---|---|---|---|---|---|---|---|---|---|---|"]
     for r in rows:
         if r.get("golden"):
             continue
         se = r["scalar_err"]
         md.append(f'| {r["case"]} | {r["n_events"]} | {r["p_err"]:.1e} | {r["m_err"]:.1e} | {se.get("est_temperature", 0):.1e} | '
-                  f'{se.get("est_config_temp", 0):.1e} | {r["de_term_err"]:.1e} | {r["de_scale"]:.0f} | {r["decisions_equal"]}/{r["decisions"]} | {r["rejections"]} |')
+                  f'{se.get("est_config_temp", 0):.1e} | {r["de_term_err"]:.1e} | {r["de_scale"]:.0f} | {r["decisions_equal"]}/{r["decisions"]} | {r["rejections"]} | {r.get("kink_guards", 0)} |')
     md += ["", "## Compact goldens at the real segment tables (`tests/test_cuda_real_tables.py`)", "",
            "Reference sampler on CPU (recorded as seeds + fingerprints) vs the CUDA sampler; `+fused_prior` = prior evaluated by the kernel.", "",
            "| case | events | strided samples | moments | ΔE (terms) | decisions equal | rejections | worst scalar |", "|---|---|---|---|---|---|---|---|"]
